@@ -1,0 +1,272 @@
+// clodb200 C ABI (include/clodb200.h): argument checking, host<->device staging, error translation.
+#include "../../include/clodb200.h"
+#include "clodb.h"
+
+#include <mutex>
+
+using namespace clodb;
+
+namespace
+{
+thread_local std::string t_last_error;
+std::mutex g_api_mutex;
+bool g_initialized = false;
+Workspace g_ws;
+
+int fail(int code, const std::string& message)
+{
+	t_last_error = message;
+	return code;
+}
+
+void ensure_workspace(size_t persist_bytes, size_t temp_bytes)
+{
+	if (g_ws.persist.capacity < persist_bytes)
+		g_ws.persist.init(persist_bytes);
+	if (g_ws.temp.capacity < temp_bytes)
+		g_ws.temp.init(temp_bytes);
+	g_ws.persist.release(0);
+	g_ws.temp.release(0);
+}
+
+Config to_config(const clodb200_config* c)
+{
+	Config r;
+	if (!c)
+		return r;
+	r.max_vertices = u32(c->max_vertices);
+	r.min_triangles = u32(c->min_triangles);
+	r.max_triangles = u32(c->max_triangles);
+	r.cluster_fill_weight = c->cluster_fill_weight;
+	r.partition_size = u32(c->partition_size);
+	r.partition_max_refined_groups = u32(c->partition_max_refined_groups);
+	r.partition_sort = c->partition_sort;
+	r.partition_spatial = c->partition_spatial;
+	r.simplify_ratio = c->simplify_ratio;
+	r.simplify_threshold = c->simplify_threshold;
+	r.simplify_error_merge_previous = c->simplify_error_merge_previous;
+	r.simplify_error_merge_additive = c->simplify_error_merge_additive;
+	r.simplify_error_factor_sloppy = c->simplify_error_factor_sloppy;
+	r.simplify_permissive = c->simplify_permissive;
+	r.simplify_fallback_sloppy = c->simplify_fallback_sloppy;
+	r.optimize_clusters = c->optimize_clusters;
+	r.optimize_bounds = c->optimize_bounds;
+	return r;
+}
+
+// tightly packed device copy of strided host positions
+float* upload_positions(const float* positions, size_t vertex_count, size_t stride_bytes, Arena& arena)
+{
+	float* dev = arena.alloc<float>(vertex_count * 3);
+	if (stride_bytes == 12)
+	{
+		dev_h2d(dev, positions, vertex_count * 12);
+	}
+	else
+	{
+		std::vector<float> packed(vertex_count * 3);
+		size_t stride = stride_bytes / 4;
+		for (size_t i = 0; i < vertex_count; ++i)
+		{
+			packed[i * 3 + 0] = positions[i * stride + 0];
+			packed[i * 3 + 1] = positions[i * stride + 1];
+			packed[i * 3 + 2] = positions[i * stride + 2];
+		}
+		dev_h2d(dev, packed.data(), vertex_count * 12);
+	}
+	return dev;
+}
+
+template <typename F>
+int guarded(F&& body)
+{
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (!g_initialized)
+		return fail(CLODB200_ERR_NO_DEVICE, "clodb200: not initialised (call clodb200_init; a CUDA device is required, there is no CPU path)");
+	try
+	{
+		return body();
+	}
+	catch (const std::exception& e)
+	{
+		return fail(CLODB200_ERR_RUNTIME, e.what());
+	}
+}
+} // namespace
+
+extern "C"
+{
+
+const char* clodb200_last_error(void)
+{
+	return t_last_error.c_str();
+}
+
+int clodb200_init(int device)
+{
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (g_initialized)
+		return CLODB200_OK;
+#ifndef CLODB_EMU
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(CLODB200_ERR_NO_DEVICE, std::string("clodb200: no CUDA device available (") + cudaGetErrorString(e) + "); there is no CPU path");
+	if (device < 0 || device >= count)
+		return fail(CLODB200_ERR_INVALID, "clodb200: invalid device ordinal");
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess)
+		return fail(CLODB200_ERR_NO_DEVICE, std::string("clodb200: cudaSetDevice failed: ") + cudaGetErrorString(e));
+	cudaStream_t s;
+	e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+	if (e != cudaSuccess)
+		return fail(CLODB200_ERR_NO_DEVICE, std::string("clodb200: stream creation failed: ") + cudaGetErrorString(e));
+	g_stream = s;
+	if (const char* dbg = getenv("CLODB200_SYNC_DEBUG"))
+		g_sync_debug = atoi(dbg);
+#else
+	(void)device;
+	if (const char* rev = getenv("CLODB200_EMU_REVERSE"))
+		emu_reverse = atoi(rev);
+#endif
+	g_initialized = true;
+	return CLODB200_OK;
+}
+
+void clodb200_shutdown(void)
+{
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (!g_initialized)
+		return;
+	g_ws.persist.destroy();
+	g_ws.temp.destroy();
+#ifndef CLODB_EMU
+	cudaStreamDestroy(g_stream);
+	g_stream = 0;
+#endif
+	g_initialized = false;
+}
+
+uint64_t clodb200_launch_count(void)
+{
+	return g_launches;
+}
+
+clodb200_config clodb200_builderConfig(void)
+{
+	clodb200_config c;
+	memset(&c, 0, sizeof(c));
+	c.max_vertices = 128;
+	c.min_triangles = 64;
+	c.max_triangles = 128;
+	c.partition_spatial = true;
+	c.partition_sort = true;
+	c.partition_size = 384;
+	c.partition_max_refined_groups = 8;
+	c.cluster_spatial = true;
+	c.cluster_fill_weight = 0.5f;
+	c.cluster_split_factor = 2.0f;
+	c.simplify_ratio = 0.5f;
+	c.simplify_threshold = 0.85f;
+	c.simplify_error_merge_previous = 1.5f;
+	c.simplify_error_merge_additive = 0.0f;
+	c.simplify_error_factor_sloppy = 100.f;
+	c.simplify_permissive = true;
+	c.simplify_fallback_permissive = false;
+	c.simplify_fallback_sloppy = true;
+	c.simplify_regularize = false;
+	c.optimize_bounds = true;
+	c.optimize_clusters = true;
+	return c;
+}
+
+int clodb200_generatePositionRemap(unsigned int* remap, const float* positions, size_t vertex_count, size_t positions_stride)
+{
+	return guarded([&]() -> int {
+		if (vertex_count == 0)
+			return CLODB200_OK;
+		if (!remap || !positions || positions_stride < 12 || positions_stride % 4)
+			return fail(CLODB200_ERR_INVALID, "clodb200_generatePositionRemap: invalid arguments");
+		ensure_workspace(vertex_count * 16 + (1 << 20), vertex_count * 40 + (1 << 20));
+		float* dpos = upload_positions(positions, vertex_count, positions_stride, g_ws.persist);
+		u32* dremap = g_ws.persist.alloc<u32>(vertex_count);
+		position_remap(dpos, vertex_count, dremap, g_ws.temp);
+		dev_d2h(remap, dremap, vertex_count * sizeof(u32));
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_clusterize(const clodb200_config* config, const unsigned int* indices, size_t index_count, const unsigned int* segment_offsets, size_t segment_count,
+    const float* positions, size_t vertex_count, size_t positions_stride,
+    unsigned int* cluster_index_counts, unsigned int* cluster_vertex_counts, unsigned int* cluster_segments, unsigned int* out_indices, size_t* out_cluster_count)
+{
+	return guarded([&]() -> int {
+		if (out_cluster_count)
+			*out_cluster_count = 0;
+		if (index_count == 0)
+			return CLODB200_OK;
+		if (!indices || !positions || index_count % 3 || positions_stride < 12 || positions_stride % 4 || !out_indices || !out_cluster_count)
+			return fail(CLODB200_ERR_INVALID, "clodb200_clusterize: invalid arguments");
+		for (size_t i = 0; i < index_count; ++i)
+			if (indices[i] >= vertex_count)
+				return fail(CLODB200_ERR_INVALID, "clodb200_clusterize: index out of range");
+		u32 T = u32(index_count / 3);
+		std::vector<u32> segs;
+		if (segment_offsets && segment_count)
+			segs.assign(segment_offsets, segment_offsets + segment_count + 1);
+		else
+			segs = {0u, T};
+		if (segs.front() != 0 || segs.back() != T)
+			return fail(CLODB200_ERR_INVALID, "clodb200_clusterize: segment offsets must cover [0, triangle_count]");
+
+		ensure_workspace(vertex_count * 12 + index_count * 12 + (16 << 20), size_t(T) * 160 + (16 << 20));
+		float* dpos = upload_positions(positions, vertex_count, positions_stride, g_ws.persist);
+		u32* dtri = g_ws.persist.alloc<u32>(index_count);
+		dev_h2d(dtri, indices, index_count * sizeof(u32));
+
+		ClusterSet cs = clusterize(dtri, T, segs.data(), u32(segs.size() - 1), dpos, to_config(config), g_ws);
+
+		std::vector<u32> offsets = dev_download(cs.cluster_tri_offset, size_t(cs.cluster_count) + 1);
+		for (u32 c = 0; c < cs.cluster_count; ++c)
+			if (cluster_index_counts)
+				cluster_index_counts[c] = (offsets[c + 1] - offsets[c]) * 3;
+		if (cluster_vertex_counts)
+			dev_d2h(cluster_vertex_counts, cs.cluster_vertex_count, size_t(cs.cluster_count) * sizeof(u32));
+		if (cluster_segments)
+			dev_d2h(cluster_segments, cs.cluster_segment, size_t(cs.cluster_count) * sizeof(u32));
+		dev_d2h(out_indices, cs.tri, index_count * sizeof(u32));
+		*out_cluster_count = cs.cluster_count;
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_computeClusterBounds(const unsigned int* indices, const unsigned int* cluster_index_counts, size_t cluster_count,
+    const float* positions, size_t vertex_count, size_t positions_stride, float* out_bounds4)
+{
+	return guarded([&]() -> int {
+		if (cluster_count == 0)
+			return CLODB200_OK;
+		if (!indices || !cluster_index_counts || !positions || !out_bounds4 || positions_stride < 12 || positions_stride % 4)
+			return fail(CLODB200_ERR_INVALID, "clodb200_computeClusterBounds: invalid arguments");
+		std::vector<u32> offsets(cluster_count + 1, 0);
+		for (size_t c = 0; c < cluster_count; ++c)
+		{
+			if (cluster_index_counts[c] % 3 || cluster_index_counts[c] > 128 * 3)
+				return fail(CLODB200_ERR_INVALID, "clodb200_computeClusterBounds: clusters must hold at most 128 triangles");
+			offsets[c + 1] = offsets[c] + cluster_index_counts[c] / 3;
+		}
+		size_t index_count = size_t(offsets.back()) * 3;
+		ensure_workspace(vertex_count * 12 + index_count * 4 + cluster_count * 24 + (16 << 20), 1 << 20);
+		float* dpos = upload_positions(positions, vertex_count, positions_stride, g_ws.persist);
+		u32* dtri = g_ws.persist.alloc<u32>(index_count);
+		dev_h2d(dtri, indices, index_count * sizeof(u32));
+		u32* doff = g_ws.persist.alloc<u32>(cluster_count + 1);
+		dev_h2d(doff, offsets.data(), offsets.size() * sizeof(u32));
+		float* dbounds = g_ws.persist.alloc<float>(cluster_count * 4);
+		cluster_bounds(dtri, doff, u32(cluster_count), dpos, dbounds);
+		dev_d2h(out_bounds4, dbounds, cluster_count * 4 * sizeof(float));
+		return CLODB200_OK;
+	});
+}
+
+} // extern "C"

@@ -1,0 +1,79 @@
+// clodb200 internal stage API (device pointers unless stated otherwise). One translation unit per stage; the C ABI in
+// capi.cu and the DAG driver in dag.cu are built on these.
+#pragma once
+
+#include "prims.cuh"
+
+namespace clodb
+{
+
+// Builder configuration actually consumed by the stages; mirrors the reference's clodConfig fields
+// (clusterlod.h:15-71) that are live on the BasicRenderer path (ClusterLODUtilities.cpp:5426-5460).
+struct Config
+{
+	u32 max_vertices = 128;
+	u32 min_triangles = 64;
+	u32 max_triangles = 128;
+	float cluster_fill_weight = 0.5f;
+	u32 partition_size = 384;
+	u32 partition_max_refined_groups = 8;
+	bool partition_sort = true;
+	bool partition_spatial = true;
+	float simplify_ratio = 0.5f;
+	float simplify_threshold = 0.85f;
+	float simplify_error_merge_previous = 1.5f;
+	float simplify_error_merge_additive = 0.0f;
+	float simplify_error_factor_sloppy = 100.f;
+	bool simplify_permissive = true;
+	bool simplify_fallback_sloppy = true;
+	bool optimize_clusters = true;
+	bool optimize_bounds = true;
+};
+
+// Device-resident input mesh (positions/attributes are tightly packed copies made at upload).
+struct DeviceMesh
+{
+	const float* positions = nullptr; // 3 floats per vertex
+	size_t vertex_count = 0;
+	const float* attributes = nullptr; // attribute_stride floats per vertex (may be null)
+	u32 attribute_stride = 0;          // floats per vertex in `attributes`
+	u32 attribute_count = 0;           // leading floats used for simplification
+	float attribute_weights[32] = {};
+	u32 attribute_protect_mask = 0;
+	const u8* vertex_lock = nullptr;
+};
+
+struct Workspace
+{
+	Arena persist; // level outputs, kept until the build finishes
+	Arena temp;    // stage temporaries, stack discipline
+};
+
+// ---- S1: position remap + protect bits (remap.cu) ----------------------------------------------------------------
+// remap[i] = lowest j with bit-equal-under-== position (meshopt_generatePositionRemap, indexgenerator.cpp:442-465)
+void position_remap(const float* positions, size_t vertex_count, u32* remap, Arena& temp);
+// locks[i] |= 2 where a protected attribute differs from the canonical vertex (clusterlod.h:829-841)
+void protect_bits(const float* attributes, u32 attribute_stride, u32 protect_mask, const u32* remap, size_t vertex_count, u8* locks);
+
+// ---- S3: spatial clusterization (clusterize.cu) ---------------------------------------------------------------------
+// Splits every segment [seg_offsets[s], seg_offsets[s+1]) of the triangle list independently into meshlets, exactly as
+// clod::clusterize -> meshopt_buildMeshletsSpatial + meshopt_optimizeMeshlet would for that segment's index list
+// (clusterlod.h:305-348; clusterizer.cpp:1380-1477, 1051-1124, 1682-1770).
+struct ClusterSet
+{
+	u32 cluster_count = 0;
+	u32 triangle_count = 0;
+	u32* tri = nullptr;             // 3 u32 per triangle, cluster-major, optimized order
+	u32* cluster_tri_offset = nullptr; // cluster_count + 1, in triangles
+	u32* cluster_vertex_count = nullptr;
+	u32* cluster_segment = nullptr; // source segment of each cluster
+};
+ClusterSet clusterize(const u32* tri, u32 triangle_count, const u32* seg_offsets_host, u32 segment_count, const float* positions, const Config& config, Workspace& ws);
+
+// ---- S7: bounds (bounds.cu) -----------------------------------------------------------------------------------------
+// per-cluster sphere of meshopt_computeClusterBounds (clusterizer.cpp:1479-1632); bounds = {cx,cy,cz,r} per cluster
+void cluster_bounds(const u32* tri, const u32* cluster_tri_offset, u32 cluster_count, const float* positions, float* bounds4);
+// sphere-of-spheres per group as clod::boundsMerge (clusterlod.h:283-303): out5 = {c, r, max error}
+void group_bounds_merge(const float* cluster_bounds5, const u32* group_cluster_offset, const u32* group_clusters, u32 group_count, float* out5);
+
+} // namespace clodb

@@ -1,0 +1,1070 @@
+// S3: spatial clusterization (meshlet building) for a batch of independent triangle segments.
+//
+// Reference semantics: clod::clusterize (clusterlod.h:305-348) -> meshopt_buildMeshletsSpatial
+// (ThirdParty/meshoptimizer/src/clusterizer.cpp:1380-1477) -> bvhSplit (:1051-1124), bvhPivot (:985-1033),
+// bvhComputeArea/boxMerge (:970-983, :764-805), bvhPackTail (:940-960), then meshopt_optimizeMeshlet (:1682-1770).
+//
+// B200 formulation. The reference recurses depth-first over one segment; here every tree level of every segment is
+// processed breadth-first by flat kernels over the three axis orders:
+//   - axis orders come from a stable LSD radix sort on (segment, radixFloat(centroid) >> 2), identical to the
+//     reference's 3x10-bit radix (which drops the 2 LSBs and is stable);
+//   - prefix/suffix surface areas are segmented min/max scans over the node ranges (min/max are exact and associative,
+//     so the parallel scan reproduces the sequential accumulation bit for bit);
+//   - the SAH+fill pivot is an argmin over (cost, axis, index) keys, which equals the reference's "first strictly
+//     smaller cost wins" scan order;
+//   - the stable two-way partition of the other axes is a global exclusive scan of side flags;
+//   - nodes of <= max_triangles triangles (leaf tests, vertex-bound splits, tails) are resolved by one thread each.
+// Result: the same meshlets, in the same order, with the same optimized triangle/vertex order as the reference.
+#include "clodb.h"
+
+#include <cfloat>
+#include <algorithm>
+
+namespace clodb
+{
+
+static const u32 NODE_DONE = 0xffffffffu;
+static const int kMeshletMaxTreeDepth = 50; // clusterizer.cpp:40
+
+struct Box
+{
+	float min[4];
+	float max[4];
+};
+
+struct SplitParams
+{
+	u32 max_vertices, min_triangles, max_triangles;
+	float fill_weight;
+};
+
+DEVFN u32 radix_float(u32 v)
+{
+	u32 mask = u32(int(v) >> 31) | 0x80000000u;
+	return v ^ mask;
+}
+
+// clusterizer.cpp:876-902 (bvhPrepare); the centroid key is what the reference's radix passes sort by
+KERNEL k_prepare(const u32* __restrict__ tri, const float* __restrict__ positions, u32 T, Box* boxes, u32* key0, u32* key1, u32* key2)
+{
+	size_t i = GTID;
+	if (i >= T)
+		return;
+	u32 a = tri[i * 3 + 0], b = tri[i * 3 + 1], c = tri[i * 3 + 2];
+	const float* va = positions + size_t(a) * 3;
+	const float* vb = positions + size_t(b) * 3;
+	const float* vc = positions + size_t(c) * 3;
+	Box box;
+	u32 keys[3];
+	for (int k = 0; k < 3; ++k)
+	{
+		float mn = va[k] < vb[k] ? va[k] : vb[k];
+		mn = vc[k] < mn ? vc[k] : mn;
+		float mx = va[k] > vb[k] ? va[k] : vb[k];
+		mx = vc[k] > mx ? vc[k] : mx;
+		box.min[k] = mn;
+		box.max[k] = mx;
+		float centroid = (mn + mx) / 2.f;
+		keys[k] = radix_float(__float_as_uint(centroid)) >> 2;
+	}
+	box.min[3] = 0.f;
+	box.max[3] = 0.f;
+	boxes[i] = box;
+	key0[i] = keys[0];
+	key1[i] = keys[1];
+	key2[i] = keys[2];
+}
+
+KERNEL k_widen_keys(const u32* __restrict__ key32, const u32* __restrict__ seg_of_tri, u64* key64, u32 T)
+{
+	size_t i = GTID;
+	if (i >= T)
+		return;
+	key64[i] = (u64(seg_of_tri[i]) << 30) | key32[i];
+}
+
+KERNEL k_segment_of_tri(const u32* __restrict__ seg_offsets, u32 S, u32* seg_of_tri, u32 T)
+{
+	size_t i = GTID;
+	if (i >= T)
+		return;
+	u32 lo = 0, hi = S; // find s with seg_offsets[s] <= i < seg_offsets[s+1]
+	while (hi - lo > 1)
+	{
+		u32 mid = (lo + hi) / 2;
+		if (seg_offsets[mid] <= u32(i))
+			lo = mid;
+		else
+			hi = mid;
+	}
+	seg_of_tri[i] = lo;
+}
+
+KERNEL k_init_nodes(const u32* __restrict__ seg_offsets, u32 S, u32* node_begin, u32* node_count, u32* node_of_pos)
+{
+	size_t s = GTID;
+	if (s >= S)
+		return;
+	node_begin[s] = seg_offsets[s];
+	node_count[s] = seg_offsets[s + 1] - seg_offsets[s];
+}
+
+KERNEL k_init_node_of_pos(const u32* __restrict__ seg_of_tri_sorted_pos, u32* node_of_pos, u32 T)
+{
+	size_t i = GTID;
+	if (i >= T)
+		return;
+	node_of_pos[i] = seg_of_tri_sorted_pos[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small per-thread open-addressing set of vertex ids (<= 3 * 128 insertions)
+struct VertexSet
+{
+	u32 slots[512];
+
+	DEVFN void clear(VertexSet& s)
+	{
+		for (int i = 0; i < 512; ++i)
+			s.slots[i] = 0xffffffffu;
+	}
+	// returns 1 when v was not present
+	DEVFN u32 insert(VertexSet& s, u32 v)
+	{
+		u32 h = (v * 0x9E3779B1u) >> 23;
+		for (;;)
+		{
+			u32 cur = s.slots[h];
+			if (cur == v)
+				return 0;
+			if (cur == 0xffffffffu)
+			{
+				s.slots[h] = v;
+				return 1;
+			}
+			h = (h + 1) & 511;
+		}
+	}
+};
+
+DEVFN float box_area_merge(float* mn, float* mx, const Box& other)
+{
+	for (int k = 0; k < 3; ++k)
+	{
+		mn[k] = mn[k] < other.min[k] ? mn[k] : other.min[k];
+		mx[k] = mx[k] > other.max[k] ? mx[k] : other.max[k];
+	}
+	float sx = mx[0] - mn[0], sy = mx[1] - mn[1], sz = mx[2] - mn[2];
+	// summation order of the SSE2 boxMerge the reference is compiled with on x86-64 (clusterizer.cpp:764-782)
+	return (sx * sy + sy * sz) + sz * sx;
+}
+
+DEVFN bool bvh_divisible(u32 count, u32 mn, u32 mx)
+{
+	return mn * 2 <= mx ? count >= mn : count % mn <= (count / mn) * (mx - mn);
+}
+
+// SAH + fill cost of splitting after local index i (clusterizer.cpp:985-1033); returns false when not admissible
+DEVFN bool pivot_cost(u32 i, u32 count, u32 mn, u32 mx, bool aligned, float larea, float rarea, u32 lfill_v, bool has_vertices, float fill, u32 maxfill, float* out_cost)
+{
+	u32 lsplit = i + 1, rsplit = count - (i + 1);
+	if (!bvh_divisible(lsplit, mn, mx))
+		return false;
+	if (aligned && !bvh_divisible(rsplit, mn, mx))
+		return false;
+	float cost = larea * float(int(lsplit)) + rarea * float(int(rsplit));
+	u32 lfill = has_vertices ? lfill_v : lsplit;
+	u32 rfill = has_vertices ? lfill_v : rsplit;
+	float rmaxfill = 1.f / float(int(maxfill));
+	int lrest = int(float(int(lfill + maxfill - 1)) * rmaxfill) * int(maxfill) - int(lfill);
+	int rrest = int(float(int(rfill + maxfill - 1)) * rmaxfill) * int(maxfill) - int(rfill);
+	cost += fill * (float(lrest) * larea + float(rrest) * rarea);
+	*out_cost = cost;
+	return true;
+}
+
+// bvhPackTail (clusterizer.cpp:940-960) on positions [begin, begin+count) of order
+DEVFN void pack_tail(u8* boundary, const u32* order, const u32* tri, u32 begin, u32 count, u32 max_vertices, u32 max_triangles, VertexSet& set)
+{
+	for (u32 i = 0; i < count;)
+	{
+		u32 chunk = i + max_triangles <= count ? max_triangles : count - i;
+		VertexSet::clear(set);
+		u32 used = 0;
+		for (u32 j = 0; j < chunk; ++j)
+		{
+			u32 t = order[begin + i + j];
+			used += VertexSet::insert(set, tri[size_t(t) * 3 + 0]);
+			used += VertexSet::insert(set, tri[size_t(t) * 3 + 1]);
+			used += VertexSet::insert(set, tri[size_t(t) * 3 + 2]);
+		}
+		u32 take = used <= max_vertices ? chunk : max_vertices / 3;
+		boundary[begin + i] = 1;
+		for (u32 j = 1; j < take; ++j)
+			boundary[begin + i + j] = 0;
+		i += take;
+	}
+}
+
+// Nodes that fit the triangle limit: leaf test, vertex-bound split or tail, all by one thread (bvhSplit for
+// count <= max_triangles; the reference's recursion at this size touches <= 128 triangles per node).
+// Large nodes that hit the depth limit or found no admissible split are packed here as well.
+KERNEL k_resolve_nodes(const u32* __restrict__ node_begin, const u32* __restrict__ node_count, u64* node_best, u32* node_split, u32 node_total, int depth,
+    const u32* __restrict__ order0, const u32* __restrict__ order1, const u32* __restrict__ order2, const Box* __restrict__ boxes, const u32* __restrict__ tri, u8* boundary, SplitParams sp, int pass)
+{
+	size_t n = GTID;
+	if (n >= node_total)
+		return;
+	u32 begin = node_begin[n], count = node_count[n];
+	VertexSet set;
+
+	if (pass == 1)
+	{
+		// after the scan-based pivot search over large nodes: no admissible split or depth limit => tail
+		if (count <= sp.max_triangles)
+			return;
+		u64 best = node_best[n];
+		if (best == ~u64(0) || depth >= kMeshletMaxTreeDepth)
+		{
+			pack_tail(boundary, order0, tri, begin, count, sp.max_vertices, sp.max_triangles, set);
+			node_split[n] = 0;
+		}
+		else
+		{
+			node_split[n] = u32(best & 0x3fffffffu) + 1;
+		}
+		return;
+	}
+
+	if (count > sp.max_triangles)
+		return;
+
+	const u32* orders[3] = {order0, order1, order2};
+
+	// leaf test (clusterizer.cpp:1053-1054)
+	VertexSet::clear(set);
+	u32 used = 0;
+	for (u32 j = 0; j < count; ++j)
+	{
+		u32 t = order0[begin + j];
+		used += VertexSet::insert(set, tri[size_t(t) * 3 + 0]);
+		used += VertexSet::insert(set, tri[size_t(t) * 3 + 1]);
+		used += VertexSet::insert(set, tri[size_t(t) * 3 + 2]);
+	}
+	if (used <= sp.max_vertices)
+	{
+		boundary[begin] = 1;
+		for (u32 j = 1; j < count; ++j)
+			boundary[begin + j] = 0;
+		node_split[n] = 0;
+		node_best[n] = ~u64(0);
+		return;
+	}
+
+	// vertex bound: split with vertex-fill cost (clusterizer.cpp:1061-1092)
+	u32 mint = sp.max_vertices / 3 < sp.min_triangles ? sp.max_vertices / 3 : sp.min_triangles;
+	u32 maxfill = sp.max_vertices;
+	bool aligned = count >= mint * 2 && bvh_divisible(count, mint, sp.max_triangles);
+	u32 end = aligned ? count - mint : count - 1;
+
+	int bestk = -1;
+	u32 bestsplit = 0;
+	float bestcost = FLT_MAX;
+
+	float lareas[128];
+	u32 lverts[128];
+
+	for (int k = 0; k < 3; ++k)
+	{
+		const u32* order = orders[k];
+		float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		VertexSet::clear(set);
+		u32 vcount = 0;
+		for (u32 j = 0; j < count; ++j)
+		{
+			u32 t = order[begin + j];
+			lareas[j] = box_area_merge(mn, mx, boxes[t]);
+			vcount += VertexSet::insert(set, tri[size_t(t) * 3 + 0]);
+			vcount += VertexSet::insert(set, tri[size_t(t) * 3 + 1]);
+			vcount += VertexSet::insert(set, tri[size_t(t) * 3 + 2]);
+			lverts[j] = vcount;
+		}
+		// suffix areas are consumed from the right; walk candidates descending while keeping the reference's
+		// ascending "first minimum wins" rule by tracking (cost, index)
+		float rmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, rmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		float axiscost = FLT_MAX;
+		u32 axissplit = 0;
+		// rarea for candidate i covers [i+1, count-1]
+		u32 covered = count; // suffix currently covers [covered, count-1]
+		float rarea = 0.f;
+		for (u32 i = end; i-- > mint - 1 + 0;)
+		{
+			while (covered > i + 1)
+			{
+				covered--;
+				rarea = box_area_merge(rmn, rmx, boxes[order[begin + covered]]);
+			}
+			float cost;
+			if (!pivot_cost(i, count, mint, sp.max_triangles, aligned, lareas[i], rarea, lverts[i], true, sp.fill_weight, maxfill, &cost))
+				continue;
+			// ascending scan keeps the first strict minimum; descending equivalent: take when cost <= best
+			if (cost < FLT_MAX && cost <= axiscost)
+			{
+				axiscost = cost;
+				axissplit = i + 1;
+			}
+			if (i == 0)
+				break;
+		}
+		if (axissplit && axiscost < bestcost)
+		{
+			bestk = k;
+			bestcost = axiscost;
+			bestsplit = axissplit;
+		}
+	}
+
+	if (bestk < 0 || depth >= kMeshletMaxTreeDepth)
+	{
+		pack_tail(boundary, order0, tri, begin, count, sp.max_vertices, sp.max_triangles, set);
+		node_split[n] = 0;
+		node_best[n] = ~u64(0);
+		return;
+	}
+
+	node_split[n] = bestsplit;
+	node_best[n] = (u64(bestk) << 30) | u64(bestsplit - 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// segmented prefix / suffix surface areas over active node ranges (bvhComputeArea, clusterizer.cpp:970-983)
+
+DEVFN u32 node_of(const u32* node_of_pos, size_t p)
+{
+	return node_of_pos[p];
+}
+
+#ifdef CLODB_EMU
+static void seg_area_scan(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* out_area, u32 T, bool backward, Arena&)
+{
+	g_launches += 3;
+	float mn[3], mx[3];
+	for (u32 j = 0; j < T; ++j)
+	{
+		u32 p = backward ? T - 1 - j : j;
+		u32 n = node_of_pos[p];
+		bool head = n == NODE_DONE || (backward ? p == node_begin[n] + node_count[n] - 1 : p == node_begin[n]);
+		if (head || j == 0)
+			for (int k = 0; k < 3; ++k)
+				mn[k] = FLT_MAX, mx[k] = -FLT_MAX;
+		out_area[p] = box_area_merge(mn, mx, boxes[order[p]]);
+	}
+}
+#else
+struct ScanElem
+{
+	float mn[3], mx[3];
+	u32 flag;
+};
+
+DEVFN ScanElem scan_identity()
+{
+	ScanElem e;
+	e.mn[0] = e.mn[1] = e.mn[2] = FLT_MAX;
+	e.mx[0] = e.mx[1] = e.mx[2] = -FLT_MAX;
+	e.flag = 0;
+	return e;
+}
+
+// a then b
+DEVFN ScanElem scan_combine(const ScanElem& a, const ScanElem& b)
+{
+	if (b.flag)
+		return b;
+	ScanElem r;
+	for (int k = 0; k < 3; ++k)
+	{
+		r.mn[k] = a.mn[k] < b.mn[k] ? a.mn[k] : b.mn[k];
+		r.mx[k] = a.mx[k] > b.mx[k] ? a.mx[k] : b.mx[k];
+	}
+	r.flag = a.flag;
+	return r;
+}
+
+DEVFN ScanElem scan_shfl_up(const ScanElem& e, int d)
+{
+	ScanElem r;
+	for (int k = 0; k < 3; ++k)
+	{
+		r.mn[k] = __shfl_up_sync(0xffffffffu, e.mn[k], d);
+		r.mx[k] = __shfl_up_sync(0xffffffffu, e.mx[k], d);
+	}
+	r.flag = __shfl_up_sync(0xffffffffu, e.flag, d);
+	return r;
+}
+
+static const int SA_THREADS = 256;
+static const int SA_ITEMS = 4;
+static const int SA_TILE = SA_THREADS * SA_ITEMS;
+
+DEVFN ScanElem load_elem(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, u32 T, u32 j, bool backward)
+{
+	if (j >= T)
+		return scan_identity();
+	u32 p = backward ? T - 1 - j : j;
+	u32 n = node_of_pos[p];
+	ScanElem e;
+	const Box& b = boxes[order[p]];
+	e.mn[0] = b.min[0], e.mn[1] = b.min[1], e.mn[2] = b.min[2];
+	e.mx[0] = b.max[0], e.mx[1] = b.max[1], e.mx[2] = b.max[2];
+	e.flag = n == NODE_DONE || (backward ? p == node_begin[n] + node_count[n] - 1 : p == node_begin[n]);
+	return e;
+}
+
+// inclusive block scan of per-thread aggregates; returns the exclusive prefix for this thread; total via smem
+DEVFN ScanElem block_scan_exclusive(const ScanElem& agg, ScanElem* smem /* 8 */, ScanElem* block_total)
+{
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	ScanElem inc = agg;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		ScanElem t = scan_shfl_up(inc, d);
+		if (lane >= d)
+			inc = scan_combine(t, inc);
+	}
+	if (lane == 31)
+		smem[warp] = inc;
+	__syncthreads();
+	ScanElem warp_prefix = scan_identity();
+	for (int w = 0; w < warp; ++w)
+		warp_prefix = scan_combine(warp_prefix, smem[w]);
+	if (block_total)
+	{
+		ScanElem total = scan_identity();
+		for (int w = 0; w < SA_THREADS / 32; ++w)
+			total = scan_combine(total, smem[w]);
+		*block_total = total;
+	}
+	ScanElem ex = scan_shfl_up(inc, 1);
+	if (lane == 0)
+		ex = scan_identity();
+	__syncthreads();
+	return scan_combine(warp_prefix, ex);
+}
+
+static __global__ void k_sa_reduce(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, ScanElem* tile_agg, u32 T, int backward)
+{
+	__shared__ ScanElem smem[SA_THREADS / 32];
+	u32 base = blockIdx.x * SA_TILE + threadIdx.x * SA_ITEMS;
+	ScanElem agg = scan_identity();
+#pragma unroll
+	for (int k = 0; k < SA_ITEMS; ++k)
+		agg = scan_combine(agg, load_elem(boxes, order, node_of_pos, node_begin, node_count, T, base + k, backward != 0));
+	ScanElem total;
+	block_scan_exclusive(agg, smem, &total);
+	if (threadIdx.x == 0)
+		tile_agg[blockIdx.x] = total;
+}
+
+// exclusive scan of tile aggregates by one warp (sequential over chunks of 32)
+static __global__ void k_sa_tiles(ScanElem* tile_agg, u32 tiles)
+{
+	int lane = threadIdx.x;
+	ScanElem carry = scan_identity();
+	for (u32 base = 0; base < tiles; base += 32)
+	{
+		u32 i = base + lane;
+		ScanElem v = i < tiles ? tile_agg[i] : scan_identity();
+		ScanElem inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			ScanElem t = scan_shfl_up(inc, d);
+			if (lane >= d)
+				inc = scan_combine(t, inc);
+		}
+		ScanElem ex = scan_shfl_up(inc, 1);
+		if (lane == 0)
+			ex = scan_identity();
+		ex = scan_combine(carry, ex);
+		if (i < tiles)
+			tile_agg[i] = ex;
+		ScanElem last = scan_combine(carry, inc);
+		// broadcast lane 31's inclusive value as the next carry
+		for (int k = 0; k < 3; ++k)
+		{
+			carry.mn[k] = __shfl_sync(0xffffffffu, last.mn[k], 31);
+			carry.mx[k] = __shfl_sync(0xffffffffu, last.mx[k], 31);
+		}
+		carry.flag = __shfl_sync(0xffffffffu, last.flag, 31);
+	}
+}
+
+static __global__ void k_sa_apply(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const ScanElem* __restrict__ tile_agg, float* out_area, u32 T, int backward)
+{
+	__shared__ ScanElem smem[SA_THREADS / 32];
+	u32 base = blockIdx.x * SA_TILE + threadIdx.x * SA_ITEMS;
+	ScanElem e[SA_ITEMS];
+	ScanElem agg = scan_identity();
+#pragma unroll
+	for (int k = 0; k < SA_ITEMS; ++k)
+	{
+		e[k] = load_elem(boxes, order, node_of_pos, node_begin, node_count, T, base + k, backward != 0);
+		agg = scan_combine(agg, e[k]);
+	}
+	ScanElem prefix = scan_combine(tile_agg[blockIdx.x], block_scan_exclusive(agg, smem, nullptr));
+#pragma unroll
+	for (int k = 0; k < SA_ITEMS; ++k)
+	{
+		prefix = scan_combine(prefix, e[k]);
+		u32 j = base + k;
+		if (j < T)
+		{
+			u32 p = backward ? T - 1 - j : j;
+			float sx = prefix.mx[0] - prefix.mn[0], sy = prefix.mx[1] - prefix.mn[1], sz = prefix.mx[2] - prefix.mn[2];
+			out_area[p] = (sx * sy + sy * sz) + sz * sx;
+		}
+	}
+}
+
+static void seg_area_scan(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* out_area, u32 T, bool backward, Arena& temp)
+{
+	ArenaScope scope(temp);
+	u32 tiles = (T + SA_TILE - 1) / SA_TILE;
+	ScanElem* tile_agg = temp.alloc<ScanElem>(tiles);
+	LAUNCH_GRID(k_sa_reduce, tiles, SA_THREADS, boxes, order, node_of_pos, node_begin, node_count, tile_agg, T, backward ? 1 : 0);
+	LAUNCH_GRID(k_sa_tiles, 1, 32, tile_agg, tiles);
+	LAUNCH_GRID(k_sa_apply, tiles, SA_THREADS, boxes, order, node_of_pos, node_begin, node_count, tile_agg, out_area, T, backward ? 1 : 0);
+}
+#endif
+
+// (cost, axis, index) argmin per large node (bvhPivot over count > max_triangles, vertices == NULL)
+KERNEL k_pivot_large(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const float* __restrict__ larea, const float* __restrict__ rarea, u64* node_best, u32 T, int axis, SplitParams sp)
+{
+	size_t p = GTID;
+	if (p >= T)
+		return;
+	u32 n = node_of_pos[p];
+	if (n == NODE_DONE)
+		return;
+	u32 count = node_count[n];
+	if (count <= sp.max_triangles)
+		return;
+	u32 i = u32(p) - node_begin[n];
+	u32 mn = sp.min_triangles;
+	bool aligned = count >= mn * 2 && bvh_divisible(count, mn, sp.max_triangles);
+	u32 end = aligned ? count - mn : count - 1;
+	if (i < mn - 1 || i >= end)
+		return;
+	float cost;
+	if (!pivot_cost(i, count, mn, sp.max_triangles, aligned, larea[p], rarea[p + 1], 0, false, sp.fill_weight, sp.max_triangles, &cost))
+		return;
+	if (!(cost < FLT_MAX) || cost < 0.f)
+		return;
+	u64 key = (u64(__float_as_uint(cost)) << 32) | (u64(axis) << 30) | u64(i);
+#ifndef CLODB_EMU
+	// warp-aggregate: lanes of one warp mostly sit in the same node
+	unsigned active = __activemask();
+	unsigned peers = __match_any_sync(active, n);
+	u64 best = key;
+	for (int d = 16; d >= 1; d >>= 1)
+	{
+		u64 other = __shfl_xor_sync(active, best, d);
+		unsigned src = (threadIdx.x & 31) ^ d;
+		if (((peers >> src) & 1u) && other < best)
+			best = other;
+	}
+	// after a full xor butterfly restricted to peers the minimum may not have reached every peer; let every lane whose
+	// key equals its own reduction result publish (cheap: same address, at most a few per warp)
+	if (best == key)
+		atomicMin(reinterpret_cast<unsigned long long*>(&node_best[n]), (unsigned long long)key);
+#else
+	if (key < node_best[n])
+		node_best[n] = key;
+#endif
+}
+
+KERNEL k_reset_best(u64* node_best, u32 n_nodes)
+{
+	size_t n = GTID;
+	if (n >= n_nodes)
+		return;
+	node_best[n] = ~u64(0);
+}
+
+// side flag per triangle for split nodes, read along the node's best axis (clusterizer.cpp:1098-1104)
+KERNEL k_mark_sides(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_split, const u64* __restrict__ node_best,
+    const u32* __restrict__ order0, const u32* __restrict__ order1, const u32* __restrict__ order2, u8* side, u32 T)
+{
+	size_t p = GTID;
+	if (p >= T)
+		return;
+	u32 n = node_of_pos[p];
+	if (n == NODE_DONE)
+		return;
+	u32 split = node_split[n];
+	if (split == 0)
+		return;
+	int axis = int((node_best[n] >> 30) & 3u);
+	const u32* order = axis == 0 ? order0 : (axis == 1 ? order1 : order2);
+	side[order[p]] = (u32(p) - node_begin[n]) >= split ? 1 : 0;
+}
+
+// zero-flags of all three axes laid out [axis][pos] for one global exclusive scan
+KERNEL k_side_flags(const u32* __restrict__ order0, const u32* __restrict__ order1, const u32* __restrict__ order2, const u8* __restrict__ side, u32* flags, u32 T)
+{
+	size_t i = GTID;
+	if (i >= size_t(T) * 3)
+		return;
+	u32 axis = u32(i / T);
+	u32 p = u32(i - size_t(axis) * T);
+	const u32* order = axis == 0 ? order0 : (axis == 1 ? order1 : order2);
+	flags[i] = side[order[p]] ? 0u : 1u;
+}
+
+// stable two-way partition of every split node, all three axes (bvhPartition, clusterizer.cpp:1035-1049)
+KERNEL k_partition(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_split,
+    const u32* __restrict__ order0, const u32* __restrict__ order1, const u32* __restrict__ order2, u32* out0, u32* out1, u32* out2,
+    const u8* __restrict__ side, const u32* __restrict__ zeros_before, u32 T)
+{
+	size_t i = GTID;
+	if (i >= size_t(T) * 3)
+		return;
+	u32 axis = u32(i / T);
+	u32 p = u32(i - size_t(axis) * T);
+	const u32* order = axis == 0 ? order0 : (axis == 1 ? order1 : order2);
+	u32* out = axis == 0 ? out0 : (axis == 1 ? out1 : out2);
+	u32 t = order[p];
+	u32 n = node_of_pos[p];
+	u32 split = n == NODE_DONE ? 0 : node_split[n];
+	if (split == 0)
+	{
+		out[p] = t;
+		return;
+	}
+	u32 begin = node_begin[n];
+	u32 zeros = zeros_before[size_t(axis) * T + p] - zeros_before[size_t(axis) * T + begin];
+	u32 local = p - begin;
+	u32 dst = side[t] ? begin + split + (local - zeros) : begin + zeros;
+	out[dst] = t;
+}
+
+KERNEL k_split_flags(const u32* __restrict__ node_split, u32* flags, u32 n_nodes)
+{
+	size_t n = GTID;
+	if (n >= n_nodes)
+		return;
+	flags[n] = node_split[n] ? 1u : 0u;
+}
+
+KERNEL k_make_children(const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const u32* __restrict__ node_split, const u32* __restrict__ child_rank,
+    u32* new_begin, u32* new_count, u32 n_nodes, u32 max_triangles, u32* any_large)
+{
+	size_t n = GTID;
+	if (n >= n_nodes)
+		return;
+	u32 split = node_split[n];
+	if (!split)
+		return;
+	u32 c = child_rank[n] * 2;
+	new_begin[c] = node_begin[n];
+	new_count[c] = split;
+	new_begin[c + 1] = node_begin[n] + split;
+	new_count[c + 1] = node_count[n] - split;
+	if (split > max_triangles || node_count[n] - split > max_triangles)
+		atomicOr(any_large, 1u);
+}
+
+KERNEL k_update_node_of_pos(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_split, const u32* __restrict__ child_rank, u32* new_node_of_pos, u32 T)
+{
+	size_t p = GTID;
+	if (p >= T)
+		return;
+	u32 n = node_of_pos[p];
+	u32 out = NODE_DONE;
+	if (n != NODE_DONE)
+	{
+		u32 split = node_split[n];
+		if (split)
+			out = child_rank[n] * 2 + ((u32(p) - node_begin[n]) >= split ? 1 : 0);
+	}
+	new_node_of_pos[p] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// meshlet assembly + meshopt_optimizeMeshlet, one thread per cluster
+
+KERNEL k_boundary_flags(const u8* __restrict__ boundary, u32* flags, u32 T)
+{
+	size_t i = GTID;
+	if (i >= T)
+		return;
+	flags[i] = boundary[i] ? 1u : 0u;
+}
+
+KERNEL k_cluster_starts(const u8* __restrict__ boundary, const u32* __restrict__ cluster_rank, u32* cluster_tri_offset, u32 T, u32 K)
+{
+	size_t i = GTID;
+	if (i > T)
+		return;
+	if (i == T)
+	{
+		cluster_tri_offset[K] = T;
+		return;
+	}
+	if (boundary[i])
+		cluster_tri_offset[cluster_rank[i]] = u32(i);
+}
+
+// Segments whose split produced more meshlets than meshopt_buildMeshletsBound allows: the reference then ignores
+// boundary marks while it is over budget and lets appendMeshlet cut on the vertex/triangle limits
+// (clusterizer.cpp:1441-1466, 362-411). Rare (triangle soups); replayed sequentially by one thread per segment.
+KERNEL k_fix_overflow_segments(const u32* __restrict__ seg_offsets, u32 S, const u32* __restrict__ rank, u32 T, u32 K, const u32* __restrict__ order0, const u32* __restrict__ tri, u8* boundary, SplitParams sp, u32* fixed_flag)
+{
+	size_t s = GTID;
+	if (s >= S)
+		return;
+	u32 begin = seg_offsets[s], end = seg_offsets[s + 1];
+	u32 meshlet_count = (end == T ? K : rank[end]) - rank[begin];
+	u32 index_count = (end - begin) * 3;
+	// clod::clusterize passes min_triangles as the bound's max_triangles (clusterlod.h:307)
+	u32 limit_vertices = (index_count + (sp.max_vertices - 2) - 1) / (sp.max_vertices - 2);
+	u32 limit_triangles = ((end - begin) + sp.min_triangles - 1) / sp.min_triangles;
+	u32 bound = limit_vertices > limit_triangles ? limit_vertices : limit_triangles;
+	if (meshlet_count <= bound)
+		return;
+	*fixed_flag = 1;
+
+	VertexSet set;
+	VertexSet::clear(set);
+	u32 vertex_count = 0, triangle_count = 0;
+	u32 meshlet_offset = 0, meshlet_pending = meshlet_count;
+	for (u32 i = begin; i < end; ++i)
+	{
+		u32 b = boundary[i];
+		bool split = i > begin && b == 1;
+		if (split && meshlet_offset + meshlet_pending >= bound)
+			split = false;
+		u32 t = order0[i];
+		u32 v0 = tri[size_t(t) * 3 + 0], v1 = tri[size_t(t) * 3 + 1], v2 = tri[size_t(t) * 3 + 2];
+		// probe without inserting: count of corners not yet in the meshlet (counted per corner, as the reference does)
+		u32 extra = 0;
+		for (int k = 0; k < 3; ++k)
+		{
+			u32 v = k == 0 ? v0 : (k == 1 ? v1 : v2);
+			u32 h = (v * 0x9E3779B1u) >> 23;
+			bool found = false;
+			for (;;)
+			{
+				u32 cur = set.slots[h];
+				if (cur == v)
+				{
+					found = true;
+					break;
+				}
+				if (cur == 0xffffffffu)
+					break;
+				h = (h + 1) & 511;
+			}
+			extra += found ? 0 : 1;
+		}
+		bool flush = vertex_count + extra > sp.max_vertices || triangle_count >= sp.max_triangles || split;
+		if (flush)
+		{
+			VertexSet::clear(set);
+			vertex_count = 0;
+			triangle_count = 0;
+			meshlet_offset++;
+		}
+		boundary[i] = (flush || i == begin) ? 1 : 0;
+		vertex_count += VertexSet::insert(set, v0);
+		vertex_count += VertexSet::insert(set, v1);
+		vertex_count += VertexSet::insert(set, v2);
+		triangle_count++;
+		meshlet_pending -= b;
+	}
+}
+
+
+KERNEL k_build_clusters(const u32* __restrict__ cluster_tri_offset, u32 K, const u32* __restrict__ order0, const u32* __restrict__ tri, const u32* __restrict__ seg_of_tri,
+    u32* tri_out, u32* cluster_vertex_count, u32* cluster_segment, int optimize)
+{
+	size_t c = GTID;
+	if (c >= K)
+		return;
+	u32 begin = cluster_tri_offset[c], count = cluster_tri_offset[c + 1] - begin;
+
+	// meshlet-local tables as appendMeshlet builds them (clusterizer.cpp:362-411): first-occurrence vertex order
+	u32 vertices[128];
+	u8 indices[128 * 3];
+	u32 vcount = 0;
+	{
+		u32 keys[512];
+		u8 vals[512];
+		for (int i = 0; i < 512; ++i)
+			keys[i] = 0xffffffffu;
+		for (u32 j = 0; j < count; ++j)
+		{
+			u32 t = order0[begin + j];
+			for (int k = 0; k < 3; ++k)
+			{
+				u32 v = tri[size_t(t) * 3 + k];
+				u32 h = (v * 0x9E3779B1u) >> 23;
+				for (;;)
+				{
+					if (keys[h] == v)
+						break;
+					if (keys[h] == 0xffffffffu)
+					{
+						keys[h] = v;
+						vals[h] = u8(vcount);
+						vertices[vcount++] = v;
+						break;
+					}
+					h = (h + 1) & 511;
+				}
+				indices[j * 3 + k] = vals[h];
+			}
+		}
+	}
+
+	if (optimize)
+	{
+		// meshopt_optimizeMeshlet (clusterizer.cpp:1682-1770)
+		u8 cache[128];
+		for (u32 i = 0; i < vcount; ++i)
+			cache[i] = 0;
+		u8 cache_last = 128;
+		const u8 cache_cutoff = 3;
+		for (u32 i = 0; i < count; ++i)
+		{
+			int next = -1;
+			int next_match = -1;
+			for (u32 j = i; j < count; ++j)
+			{
+				u8 a = indices[j * 3 + 0], b = indices[j * 3 + 1], cc = indices[j * 3 + 2];
+				int aok = u8(cache_last - cache[a]) < cache_cutoff;
+				int bok = u8(cache_last - cache[b]) < cache_cutoff;
+				int cok = u8(cache_last - cache[cc]) < cache_cutoff;
+				if (aok + bok + cok > next_match)
+				{
+					next = int(j);
+					next_match = aok + bok + cok;
+					if (next_match >= 2)
+						break;
+				}
+			}
+			u8 a = indices[next * 3 + 0], b = indices[next * 3 + 1], cc = indices[next * 3 + 2];
+			for (int j = next; j > int(i); --j)
+			{
+				indices[j * 3 + 0] = indices[(j - 1) * 3 + 0];
+				indices[j * 3 + 1] = indices[(j - 1) * 3 + 1];
+				indices[j * 3 + 2] = indices[(j - 1) * 3 + 2];
+			}
+			indices[i * 3 + 0] = a;
+			indices[i * 3 + 1] = b;
+			indices[i * 3 + 2] = cc;
+			cache_last++;
+			cache[a] = cache_last;
+			cache[b] = cache_last;
+			cache[cc] = cache_last;
+		}
+		// the vertex reorder only permutes meshlet-local ids; global ids per corner are unaffected
+	}
+
+	for (u32 j = 0; j < count * 3; ++j)
+		tri_out[size_t(begin) * 3 + j] = vertices[indices[j]];
+	cluster_vertex_count[c] = vcount;
+	cluster_segment[c] = seg_of_tri[order0[begin]];
+}
+
+KERNEL k_gather_u32(const u32* __restrict__ src, const u32* __restrict__ index, u32* dst, u32 n)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	dst[i] = src[index[i]];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S, const float* positions, const Config& config, Workspace& ws)
+{
+	ClusterSet result;
+	result.triangle_count = T;
+	if (T == 0 || S == 0)
+		return result;
+
+	Arena& temp = ws.temp;
+	ArenaScope scope(temp);
+
+	SplitParams sp;
+	sp.max_vertices = config.max_vertices;
+	sp.min_triangles = config.min_triangles;
+	sp.max_triangles = config.max_triangles;
+	sp.fill_weight = config.cluster_fill_weight;
+	if (sp.max_triangles > 128 || sp.max_vertices > 128)
+		throw Error("clodb200: clusterize supports max_triangles/max_vertices <= 128");
+
+	for (u32 s = 0; s < S; ++s)
+		if (seg_offsets_host[s + 1] <= seg_offsets_host[s])
+			throw Error("clodb200: clusterize segments must be non-empty");
+
+	u32* seg_offsets = temp.alloc<u32>(S + 1);
+	dev_h2d(seg_offsets, seg_offsets_host, (S + 1) * sizeof(u32));
+
+	Box* boxes = temp.alloc<Box>(T);
+	u32* order[3];
+	u32* order_alt[3];
+	for (int k = 0; k < 3; ++k)
+	{
+		order[k] = temp.alloc<u32>(T);
+		order_alt[k] = temp.alloc<u32>(T);
+	}
+	u32* seg_of_tri = temp.alloc<u32>(T);
+	LAUNCH(k_segment_of_tri, T, seg_offsets, S, seg_of_tri, T);
+
+	// ---- axis orders
+	{
+		ArenaScope sort_scope(temp);
+		u32* key32[3];
+		for (int k = 0; k < 3; ++k)
+			key32[k] = temp.alloc<u32>(T);
+		LAUNCH(k_prepare, T, tri, positions, T, boxes, key32[0], key32[1], key32[2]);
+		int seg_bits = S > 1 ? bits_for(S - 1) : 0;
+		if (seg_bits + 30 <= 32)
+		{
+			u32* key_tmp = temp.alloc<u32>(T);
+			for (int k = 0; k < 3; ++k)
+			{
+				iota(order[k], T);
+				radix_sort_pairs<u32>(key32[k], key_tmp, order[k], order_alt[k], T, 0, 30, temp);
+			}
+			if (seg_bits)
+			{
+				// stable pass on the segment id restores segment-major order (segments were contiguous on input)
+				u32* seg_key = temp.alloc<u32>(T);
+				u32* seg_tmp = temp.alloc<u32>(T);
+				for (int k = 0; k < 3; ++k)
+				{
+					LAUNCH(k_gather_u32, T, seg_of_tri, order[k], seg_key, T);
+					radix_sort_pairs<u32>(seg_key, seg_tmp, order[k], order_alt[k], T, 0, seg_bits, temp);
+				}
+			}
+		}
+		else
+		{
+			u64* key64 = temp.alloc<u64>(T);
+			u64* key64_tmp = temp.alloc<u64>(T);
+			for (int k = 0; k < 3; ++k)
+			{
+				LAUNCH(k_widen_keys, T, key32[k], seg_of_tri, key64, T);
+				iota(order[k], T);
+				radix_sort_pairs<u64>(key64, key64_tmp, order[k], order_alt[k], T, 0, 30 + seg_bits, temp);
+			}
+		}
+	}
+
+	// ---- breadth-first splitting
+	u32 node_cap = T / 32 + S + 2;
+	u32* node_begin = temp.alloc<u32>(node_cap);
+	u32* node_count = temp.alloc<u32>(node_cap);
+	u32* node_begin_alt = temp.alloc<u32>(node_cap);
+	u32* node_count_alt = temp.alloc<u32>(node_cap);
+	u64* node_best = temp.alloc<u64>(node_cap);
+	u32* node_split = temp.alloc<u32>(node_cap);
+	u32* node_flags = temp.alloc<u32>(node_cap);
+	u32* node_total_dev = temp.alloc<u32>(4);
+	u32* node_of_pos = temp.alloc<u32>(T);
+	u32* node_of_pos_alt = temp.alloc<u32>(T);
+	u8* boundary = temp.alloc<u8>(T);
+	u8* side = temp.alloc<u8>(T);
+	float* larea = temp.alloc<float>(size_t(T) + 1);
+	float* rarea = temp.alloc<float>(size_t(T) + 1);
+	u32* flags3 = temp.alloc<u32>(size_t(T) * 3);
+
+	LAUNCH(k_init_nodes, S, seg_offsets, S, node_begin, node_count, node_of_pos);
+	// positions are segment-major after the sort, so position p belongs to the segment of any triangle stored there
+	LAUNCH(k_gather_u32, T, seg_of_tri, order[0], node_of_pos, T);
+	dev_memset(boundary, 0, T);
+
+	u32 n_nodes = S;
+	u32 max_count = 0;
+	for (u32 s = 0; s < S; ++s)
+		max_count = std::max(max_count, seg_offsets_host[s + 1] - seg_offsets_host[s]);
+	bool any_large = max_count > sp.max_triangles;
+
+	for (int depth = 0; n_nodes > 0; ++depth)
+	{
+		if (n_nodes > node_cap)
+			throw Error("clodb200: clusterize node capacity exceeded");
+
+		LAUNCH(k_reset_best, n_nodes, node_best, n_nodes);
+		dev_memset(node_split, 0, size_t(n_nodes) * sizeof(u32));
+
+		if (any_large)
+		{
+			for (int k = 0; k < 3; ++k)
+			{
+				seg_area_scan(boxes, order[k], node_of_pos, node_begin, node_count, larea, T, false, temp);
+				seg_area_scan(boxes, order[k], node_of_pos, node_begin, node_count, rarea, T, true, temp);
+				LAUNCH(k_pivot_large, T, node_of_pos, node_begin, node_count, larea, rarea, node_best, T, k, sp);
+			}
+			LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 1);
+		}
+		LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 0);
+
+		// children numbering
+		LAUNCH(k_split_flags, n_nodes, node_split, node_flags, n_nodes);
+		exclusive_scan_u32(node_flags, node_flags, n_nodes, node_total_dev, temp);
+		u32 n_split = dev_read(node_total_dev);
+		if (n_split == 0)
+			break;
+
+		LAUNCH(k_mark_sides, T, node_of_pos, node_begin, node_split, node_best, order[0], order[1], order[2], side, T);
+		LAUNCH(k_side_flags, size_t(T) * 3, order[0], order[1], order[2], side, flags3, T);
+		exclusive_scan_u32(flags3, flags3, size_t(T) * 3, nullptr, temp);
+		LAUNCH(k_partition, size_t(T) * 3, node_of_pos, node_begin, node_split, order[0], order[1], order[2], order_alt[0], order_alt[1], order_alt[2], side, flags3, T);
+		dev_memset(node_total_dev + 1, 0, sizeof(u32));
+		LAUNCH(k_make_children, n_nodes, node_begin, node_count, node_split, node_flags, node_begin_alt, node_count_alt, n_nodes, sp.max_triangles, node_total_dev + 1);
+		LAUNCH(k_update_node_of_pos, T, node_of_pos, node_begin, node_split, node_flags, node_of_pos_alt, T);
+
+		for (int k = 0; k < 3; ++k)
+			std::swap(order[k], order_alt[k]);
+		std::swap(node_begin, node_begin_alt);
+		std::swap(node_count, node_count_alt);
+		std::swap(node_of_pos, node_of_pos_alt);
+		n_nodes = n_split * 2;
+		any_large = dev_read(node_total_dev + 1) != 0;
+		if (depth > kMeshletMaxTreeDepth + 2)
+			throw Error("clodb200: clusterize exceeded the tree depth limit");
+	}
+
+	// ---- meshlets
+	u32* rank = flags3; // reuse
+	LAUNCH(k_boundary_flags, T, boundary, rank, T);
+	exclusive_scan_u32(rank, rank, T, node_total_dev, temp);
+	u32 K = dev_read(node_total_dev);
+	{
+		dev_memset(node_total_dev + 1, 0, sizeof(u32));
+		LAUNCH(k_fix_overflow_segments, S, seg_offsets, S, rank, T, K, order[0], tri, boundary, sp, node_total_dev + 1);
+		if (dev_read(node_total_dev + 1))
+		{
+			LAUNCH(k_boundary_flags, T, boundary, rank, T);
+			exclusive_scan_u32(rank, rank, T, node_total_dev, temp);
+			K = dev_read(node_total_dev);
+		}
+	}
+
+	result.cluster_count = K;
+	result.tri = ws.persist.alloc<u32>(size_t(T) * 3);
+	result.cluster_tri_offset = ws.persist.alloc<u32>(size_t(K) + 1);
+	result.cluster_vertex_count = ws.persist.alloc<u32>(K);
+	result.cluster_segment = ws.persist.alloc<u32>(K);
+
+	LAUNCH(k_cluster_starts, size_t(T) + 1, boundary, rank, result.cluster_tri_offset, T, K);
+	LAUNCH(k_build_clusters, K, result.cluster_tri_offset, K, order[0], tri, seg_of_tri, result.tri, result.cluster_vertex_count, result.cluster_segment, config.optimize_clusters ? 1 : 0);
+	return result;
+}
+
+} // namespace clodb

@@ -1,0 +1,268 @@
+// clodb200 runtime layer: device memory arena, stream, kernel-launch macros.
+//
+// Product builds compile this with nvcc for sm_100a. The same kernel sources can also be compiled by g++ with
+// -DCLODB_EMU into a *development-only* host emulation (tests/emu): every kernel body is then run as a serial loop over
+// its thread index. That build exists so kernel logic can be debugged (gdb/asan) in a container without a GPU; it is
+// never linked into libclodb200.so and the product library has no CPU code path.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef CLODB_EMU
+#include <cmath>
+#include <algorithm>
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace clodb
+{
+
+struct Error : std::runtime_error
+{
+	explicit Error(const std::string& what)
+	    : std::runtime_error(what)
+	{
+	}
+};
+
+#ifdef CLODB_EMU
+// ------------------------------------------------------------------------------------------------ host emulation
+#define KERNEL static void
+#define DEVFN static inline
+#define HOSTDEVFN static inline
+#define CONSTANT static const
+
+extern size_t emu_tid;
+extern int emu_reverse;
+#define GTID (::clodb::emu_tid)
+
+#define LAUNCH(kernel, n, ...)                                               \
+	do                                                                       \
+	{                                                                        \
+		size_t _n = size_t(n);                                               \
+		::clodb::g_launches++;                                               \
+		if (::clodb::emu_reverse)                                            \
+			for (size_t _i = _n; _i-- > 0;)                                  \
+			{                                                                \
+				::clodb::emu_tid = _i;                                       \
+				kernel(__VA_ARGS__);                                         \
+			}                                                                \
+		else                                                                 \
+			for (size_t _i = 0; _i < _n; ++_i)                               \
+			{                                                                \
+				::clodb::emu_tid = _i;                                       \
+				kernel(__VA_ARGS__);                                         \
+			}                                                                \
+	} while (0)
+
+template <typename T>
+static inline T atomicAdd(T* p, T v)
+{
+	T old = *p;
+	*p = old + v;
+	return old;
+}
+template <typename T>
+static inline T atomicMin(T* p, T v)
+{
+	T old = *p;
+	if (v < old)
+		*p = v;
+	return old;
+}
+template <typename T>
+static inline T atomicMax(T* p, T v)
+{
+	T old = *p;
+	if (v > old)
+		*p = v;
+	return old;
+}
+template <typename T>
+static inline T atomicOr(T* p, T v)
+{
+	T old = *p;
+	*p = old | v;
+	return old;
+}
+template <typename T>
+static inline T atomicExch(T* p, T v)
+{
+	T old = *p;
+	*p = v;
+	return old;
+}
+template <typename T>
+static inline T atomicCAS(T* p, T cmp, T v)
+{
+	T old = *p;
+	if (old == cmp)
+		*p = v;
+	return old;
+}
+static inline unsigned int __float_as_uint(float f)
+{
+	unsigned int u;
+	memcpy(&u, &f, 4);
+	return u;
+}
+static inline float __uint_as_float(unsigned int u)
+{
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+static inline int __popc(unsigned int v)
+{
+	return __builtin_popcount(v);
+}
+static inline int __clz(unsigned int v)
+{
+	return v ? __builtin_clz(v) : 32;
+}
+template <typename T>
+static inline T __ldg(const T* p)
+{
+	return *p;
+}
+typedef void* stream_t;
+
+#else
+// ------------------------------------------------------------------------------------------------ CUDA (sm_100a)
+#define KERNEL static __global__ void
+#define DEVFN static __device__ __forceinline__
+#define HOSTDEVFN static __host__ __device__ __forceinline__
+#define CONSTANT static __constant__ const
+#define GTID (size_t(blockIdx.x) * blockDim.x + threadIdx.x)
+
+typedef cudaStream_t stream_t;
+
+#define CUDA_CHECK(expr)                                                                                                 \
+	do                                                                                                                   \
+	{                                                                                                                    \
+		cudaError_t _e = (expr);                                                                                         \
+		if (_e != cudaSuccess)                                                                                           \
+			throw ::clodb::Error(std::string("CUDA error ") + cudaGetErrorString(_e) + " at " __FILE__ ":" + std::to_string(__LINE__) + " in " #expr); \
+	} while (0)
+
+// one thread per element, 256-thread CTAs; grid rounded up (callers guard with `if (i >= n) return`)
+#define LAUNCH(kernel, n, ...)                                                                         \
+	do                                                                                                 \
+	{                                                                                                  \
+		size_t _n = size_t(n);                                                                         \
+		if (_n > 0)                                                                                    \
+		{                                                                                              \
+			kernel<<<(unsigned int)((_n + 255) / 256), 256, 0, ::clodb::g_stream>>>(__VA_ARGS__);       \
+			::clodb::g_launches++;                                                                     \
+			CUDA_CHECK(cudaGetLastError());                                                            \
+			if (::clodb::g_sync_debug)                                                                 \
+				CUDA_CHECK(cudaStreamSynchronize(::clodb::g_stream));                                  \
+		}                                                                                              \
+	} while (0)
+
+// explicit grid/block launch for cooperative (block-level) kernels
+#define LAUNCH_GRID(kernel, grid, block, ...)                                                          \
+	do                                                                                                 \
+	{                                                                                                  \
+		if ((grid) > 0)                                                                                \
+		{                                                                                              \
+			kernel<<<(unsigned int)(grid), (block), 0, ::clodb::g_stream>>>(__VA_ARGS__);              \
+			::clodb::g_launches++;                                                                     \
+			CUDA_CHECK(cudaGetLastError());                                                            \
+			if (::clodb::g_sync_debug)                                                                 \
+				CUDA_CHECK(cudaStreamSynchronize(::clodb::g_stream));                                  \
+		}                                                                                              \
+	} while (0)
+#endif
+
+extern stream_t g_stream;
+extern uint64_t g_launches;
+extern int g_sync_debug;
+
+// ---- raw device memory -------------------------------------------------------------------------------------------
+void* dev_malloc(size_t bytes);
+void dev_free(void* p);
+void dev_memset(void* p, int value, size_t bytes);
+void dev_h2d(void* dst, const void* src, size_t bytes);
+void dev_d2h(void* dst, const void* src, size_t bytes);
+void dev_d2d(void* dst, const void* src, size_t bytes);
+void dev_sync();
+
+// ---- stack arena: all per-build temporaries come from one cudaMalloc'd slab (no allocator calls inside the loop) -----
+struct Arena
+{
+	char* base = nullptr;
+	size_t capacity = 0;
+	size_t offset = 0;
+	size_t high_water = 0;
+
+	void init(size_t bytes);
+	void destroy();
+
+	size_t mark() const
+	{
+		return offset;
+	}
+	void release(size_t m)
+	{
+		offset = m;
+	}
+
+	void* alloc_bytes(size_t bytes)
+	{
+		size_t aligned = (offset + 255) & ~size_t(255);
+		if (aligned + bytes > capacity)
+			throw Error("clodb200: device arena exhausted (need " + std::to_string(aligned + bytes) + " of " + std::to_string(capacity) + " bytes)");
+		offset = aligned + bytes;
+		if (offset > high_water)
+			high_water = offset;
+		return base + aligned;
+	}
+
+	template <typename T>
+	T* alloc(size_t count)
+	{
+		return static_cast<T*>(alloc_bytes(count * sizeof(T) + 16));
+	}
+};
+
+struct ArenaScope
+{
+	Arena& arena;
+	size_t m;
+	explicit ArenaScope(Arena& a)
+	    : arena(a), m(a.mark())
+	{
+	}
+	~ArenaScope()
+	{
+		arena.release(m);
+	}
+};
+
+template <typename T>
+static inline T dev_read(const T* p)
+{
+	T v;
+	dev_d2h(&v, p, sizeof(T));
+	return v;
+}
+
+template <typename T>
+static inline std::vector<T> dev_download(const T* p, size_t count)
+{
+	std::vector<T> v(count);
+	if (count)
+		dev_d2h(v.data(), p, count * sizeof(T));
+	return v;
+}
+
+} // namespace clodb

@@ -1,0 +1,88 @@
+/* clodb200 — B200-native cluster-LOD DAG builder: C ABI.
+ *
+ * Drop-in boundary for the cluster-LOD build path of panthuncia/BasicRenderer. Every entry point takes plain pointers
+ * and sizes (no C++/torch types) and returns 0 on success or a negative status; clodb200_last_error() returns the
+ * message of the last failure on the calling thread. Pointers are HOST pointers unless the name says _device.
+ * The library has no CPU code path: every call fails with CLODB200_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   clodb200_generatePositionRemap  <- meshopt_generatePositionRemap, ThirdParty/meshoptimizer/src/meshoptimizer.h
+ *                                      (called at BasicRenderer/include/ThirdParty/meshoptimizer/clusterlod.h:826)
+ *   clodb200_clusterize             <- clod::clusterize, clusterlod.h:305-348 (meshopt_buildMeshletsSpatial +
+ *                                      meshopt_optimizeMeshlet), batched over independent index segments
+ *   clodb200_computeClusterBounds   <- meshopt_computeClusterBounds via clod::boundsCompute, clusterlod.h:270-281
+ *   clodb200_build / clodb200_buildEx <- clodBuild / clodBuildEx, clusterlod.h:159-184 (same structs, same callback)
+ */
+#ifndef CLODB200_H
+#define CLODB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define CLODB200_OK 0
+#define CLODB200_ERR_NO_DEVICE (-1)
+#define CLODB200_ERR_INVALID (-2)
+#define CLODB200_ERR_RUNTIME (-3)
+
+/* Same layout as struct clodConfig, clusterlod.h:15-71. */
+typedef struct clodb200_config
+{
+	size_t max_vertices;
+	size_t min_triangles;
+	size_t max_triangles;
+	bool partition_spatial;
+	bool partition_sort;
+	size_t partition_size;
+	size_t partition_max_refined_groups;
+	size_t* partition_refined_split_count;
+	bool cluster_spatial;
+	float cluster_fill_weight;
+	float cluster_split_factor;
+	float simplify_ratio;
+	float simplify_threshold;
+	float simplify_error_merge_previous;
+	float simplify_error_merge_additive;
+	float simplify_error_factor_sloppy;
+	float simplify_error_edge_limit;
+	bool simplify_permissive;
+	bool simplify_fallback_permissive;
+	bool simplify_fallback_sloppy;
+	bool simplify_regularize;
+	bool optimize_bounds;
+	bool optimize_clusters;
+} clodb200_config;
+
+const char* clodb200_last_error(void);
+/* Selects the CUDA device for this process (one process per GPU) and creates the build stream. */
+int clodb200_init(int device);
+void clodb200_shutdown(void);
+/* Kernel launches issued by this library since clodb200_init (bench.py's gpu_launches). */
+uint64_t clodb200_launch_count(void);
+
+/* clodDefaultConfig(max_triangles) followed by the BasicRenderer overrides (ClusterLODUtilities.cpp:5426-5460). */
+clodb200_config clodb200_builderConfig(void);
+
+/* remap[i] = lowest index with the same position (IEEE ==). positions_stride in bytes (>= 12, multiple of 4). */
+int clodb200_generatePositionRemap(unsigned int* remap, const float* positions, size_t vertex_count, size_t positions_stride);
+
+/* Splits each segment [segment_offsets[s], segment_offsets[s+1]) (in triangles) of `indices` into meshlets.
+ * Outputs: cluster_index_counts/cluster_vertex_counts/cluster_segments hold one entry per cluster (capacity
+ * index_count / 3 entries each), out_indices receives index_count cluster-major indices. Returns the cluster count in
+ * *out_cluster_count. segment_offsets == NULL means one segment covering everything. */
+int clodb200_clusterize(const clodb200_config* config, const unsigned int* indices, size_t index_count, const unsigned int* segment_offsets, size_t segment_count,
+    const float* positions, size_t vertex_count, size_t positions_stride,
+    unsigned int* cluster_index_counts, unsigned int* cluster_vertex_counts, unsigned int* cluster_segments, unsigned int* out_indices, size_t* out_cluster_count);
+
+/* Bounding sphere {cx, cy, cz, r} per cluster; clusters are given as cluster-major indices + per-cluster index counts. */
+int clodb200_computeClusterBounds(const unsigned int* indices, const unsigned int* cluster_index_counts, size_t cluster_count,
+    const float* positions, size_t vertex_count, size_t positions_stride, float* out_bounds4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
