@@ -68,6 +68,9 @@ class ClodLib:
         L.clodb200_generatePositionRemap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
         L.clodb200_clusterize.argtypes = [C.POINTER(Config), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         L.clodb200_computeClusterBounds.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.clodb200_lockBoundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.clodb200_simplifyGroups.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.clodb200_simplifyStats.argtypes = [C.c_void_p]
         self._check(L.clodb200_init(device))
 
     def _check(self, status: int):
@@ -114,6 +117,42 @@ class ClodLib:
         out = np.zeros((counts.size, 4), dtype=np.float32)
         self._check(self._lib.clodb200_computeClusterBounds(_ptr(indices), _ptr(counts), counts.size, _ptr(positions), positions.shape[0], positions.shape[1] * 4, _ptr(out)))
         return out
+
+
+    def lock_boundary(self, locks: np.ndarray, indices: np.ndarray, group_index_offsets: np.ndarray, remap: np.ndarray, vertex_lock=None) -> np.ndarray:
+        locks = np.ascontiguousarray(locks, dtype=np.uint8).copy()
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        offs = np.ascontiguousarray(group_index_offsets, dtype=np.uint32)
+        remap = np.ascontiguousarray(remap, dtype=np.uint32)
+        vl = None if vertex_lock is None else np.ascontiguousarray(vertex_lock, dtype=np.uint8)
+        self._check(self._lib.clodb200_lockBoundary(_ptr(locks), _ptr(indices), _ptr(offs), offs.size - 1, _ptr(remap), _ptr(vl), locks.size))
+        return locks
+
+    def simplify_groups(self, positions, indices, group_index_offsets, locks, attributes=None, attribute_weights=None, config: Config | None = None):
+        """-> (indices, group_index_offsets[G+1], group_errors[G])"""
+        cfg = config or self.builder_config()
+        positions = np.ascontiguousarray(positions, dtype=np.float32)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        offs = np.ascontiguousarray(group_index_offsets, dtype=np.uint32)
+        locks = None if locks is None else np.ascontiguousarray(locks, dtype=np.uint8)
+        G = offs.size - 1
+        acount = astride = 0
+        if attributes is not None:
+            attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+            attribute_weights = np.ascontiguousarray(attribute_weights, dtype=np.float32)
+            acount, astride = attribute_weights.size, attributes.shape[1] * 4
+        out = np.zeros(max(1, indices.size), dtype=np.uint32)
+        counts = np.zeros(G, dtype=np.uint32)
+        errors = np.zeros(G, dtype=np.float32)
+        self._check(self._lib.clodb200_simplifyGroups(C.byref(cfg), _ptr(indices), _ptr(offs), G, _ptr(positions), positions.shape[0], positions.shape[1] * 4, _ptr(attributes), astride, _ptr(attribute_weights), acount, _ptr(locks), _ptr(out), _ptr(counts), _ptr(errors)))
+        out_offs = np.zeros(G + 1, dtype=np.uint32)
+        np.cumsum(counts, out=out_offs[1:])
+        return out[: out_offs[-1]].copy(), out_offs, errors
+
+    def simplify_stats(self):
+        a = (C.c_uint * 3)()
+        self._lib.clodb200_simplifyStats(a)
+        return {"passes": a[0], "rounds": a[1], "max_rounds": a[2]}
 
 
 _product = None

@@ -269,4 +269,98 @@ int clodb200_computeClusterBounds(const unsigned int* indices, const unsigned in
 	});
 }
 
+int clodb200_lockBoundary(unsigned char* locks, const unsigned int* indices, const unsigned int* group_index_offsets, size_t group_count,
+    const unsigned int* remap, const unsigned char* vertex_lock, size_t vertex_count)
+{
+	return guarded([&]() -> int {
+		if (!locks || !indices || !group_index_offsets || !remap)
+			return fail(CLODB200_ERR_INVALID, "clodb200_lockBoundary: invalid arguments");
+		size_t index_count = group_index_offsets[group_count];
+		ensure_workspace(index_count * 4 + vertex_count * 8 + group_count * 4 + (16 << 20), vertex_count * 8 + (16 << 20));
+		std::vector<u32> tri_offsets(group_count + 1);
+		for (size_t g = 0; g <= group_count; ++g)
+			tri_offsets[g] = group_index_offsets[g] / 3;
+		u32* dtri = g_ws.persist.alloc<u32>(index_count);
+		u32* doff = g_ws.persist.alloc<u32>(group_count + 1);
+		u32* dremap = g_ws.persist.alloc<u32>(vertex_count);
+		u8* dlocks = g_ws.persist.alloc<u8>(vertex_count);
+		u8* dvlock = vertex_lock ? g_ws.persist.alloc<u8>(vertex_count) : nullptr;
+		dev_h2d(dtri, indices, index_count * 4);
+		dev_h2d(doff, tri_offsets.data(), tri_offsets.size() * 4);
+		dev_h2d(dremap, remap, vertex_count * 4);
+		dev_h2d(dlocks, locks, vertex_count);
+		if (vertex_lock)
+			dev_h2d(dvlock, vertex_lock, vertex_count);
+		lock_boundary(dtri, doff, u32(group_count), u32(index_count / 3), dremap, dvlock, vertex_count, dlocks, g_ws.temp);
+		dev_d2h(locks, dlocks, vertex_count);
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* indices, const unsigned int* group_index_offsets, size_t group_count,
+    const float* positions, size_t vertex_count, size_t positions_stride,
+    const float* attributes, size_t attributes_stride, const float* attribute_weights, size_t attribute_count,
+    const unsigned char* locks, unsigned int* out_indices, unsigned int* out_group_index_counts, float* out_group_errors)
+{
+	return guarded([&]() -> int {
+		if (group_count == 0)
+			return CLODB200_OK;
+		if (!indices || !group_index_offsets || !positions || positions_stride < 12 || positions_stride % 4 || !out_indices || !out_group_index_counts || !out_group_errors)
+			return fail(CLODB200_ERR_INVALID, "clodb200_simplifyGroups: invalid arguments");
+		if (attribute_count && (!attributes || !attribute_weights || attributes_stride < attribute_count * 4 || attributes_stride % 4 || attribute_count > 32))
+			return fail(CLODB200_ERR_INVALID, "clodb200_simplifyGroups: invalid attribute arguments");
+		size_t index_count = group_index_offsets[group_count];
+		std::vector<u32> tri_offsets(group_count + 1);
+		for (size_t g = 0; g <= group_count; ++g)
+		{
+			if (group_index_offsets[g] % 3)
+				return fail(CLODB200_ERR_INVALID, "clodb200_simplifyGroups: group offsets must be multiples of 3");
+			tri_offsets[g] = group_index_offsets[g] / 3;
+		}
+		size_t astride = attribute_count ? attributes_stride / 4 : 0;
+		ensure_workspace(vertex_count * (24 + astride * 4) + index_count * 12 + (32 << 20), index_count * 200 + vertex_count * 16 + (32 << 20));
+
+		DeviceMesh mesh;
+		float* dpos = upload_positions(positions, vertex_count, positions_stride, g_ws.persist);
+		mesh.positions = dpos;
+		mesh.vertex_count = vertex_count;
+		if (attribute_count)
+		{
+			float* dattr = g_ws.persist.alloc<float>(vertex_count * astride);
+			dev_h2d(dattr, attributes, vertex_count * astride * 4);
+			mesh.attributes = dattr;
+			mesh.attribute_stride = u32(astride);
+			mesh.attribute_count = u32(attribute_count);
+			for (size_t i = 0; i < attribute_count; ++i)
+				mesh.attribute_weights[i] = attribute_weights[i];
+		}
+		u8* dlocks = nullptr;
+		if (locks)
+		{
+			dlocks = g_ws.persist.alloc<u8>(vertex_count);
+			dev_h2d(dlocks, locks, vertex_count);
+		}
+		u32* dremap = g_ws.persist.alloc<u32>(vertex_count);
+		position_remap(dpos, vertex_count, dremap, g_ws.temp);
+		u32* dtri = g_ws.persist.alloc<u32>(index_count);
+		dev_h2d(dtri, indices, index_count * 4);
+
+		SimplifyOutput so = simplify_groups(dtri, tri_offsets.data(), u32(group_count), mesh, dremap, dlocks, to_config(config), g_ws);
+
+		std::vector<u32> offs = dev_download(so.group_tri_offset, group_count + 1);
+		for (size_t g = 0; g < group_count; ++g)
+			out_group_index_counts[g] = (offs[g + 1] - offs[g]) * 3;
+		dev_d2h(out_indices, so.tri, size_t(so.triangle_count) * 12);
+		dev_d2h(out_group_errors, so.group_error, group_count * 4);
+		return CLODB200_OK;
+	});
+}
+
+void clodb200_simplifyStats(unsigned int out3[3])
+{
+	out3[0] = g_simplify_stats.passes;
+	out3[1] = g_simplify_stats.rounds;
+	out3[2] = g_simplify_stats.max_rounds;
+}
+
 } // extern "C"

@@ -76,4 +76,31 @@ void cluster_bounds(const u32* tri, const u32* cluster_tri_offset, u32 cluster_c
 // sphere-of-spheres per group as clod::boundsMerge (clusterlod.h:283-303): out5 = {c, r, max error}
 void group_bounds_merge(const float* cluster_bounds5, const u32* group_cluster_offset, const u32* group_clusters, u32 group_count, float* out5);
 
+// ---- S5: group assembly + boundary locks (groups.cu) --------------------------------------------------------------
+// Gathers the triangles of each group (clusters listed group-major in group_clusters) into one contiguous run per group,
+// as runIterationTask's merge (clusterlod.h:708-711). Returns the per-group triangle offsets (host) in out_offsets.
+void gather_group_triangles(const u32* tri, const u32* cluster_tri_offset, const u32* group_clusters, u32 cluster_count, u32* gtri_out, u32* gc_tri_offset /* cluster_count + 1 */, Arena& temp);
+// clod::lockBoundary (clusterlod.h:512-559): bit0 = position class touched by >= 2 groups, keeps bit1 (protect), ORs vertex_lock
+void lock_boundary(const u32* gtri, const u32* tri_group_offsets_dev, u32 group_count, u32 triangle_count, const u32* remap, const u8* vertex_lock, size_t vertex_count, u8* locks, Arena& temp);
+
+// ---- S6: simplification (simplify.cu) -------------------------------------------------------------------------------
+struct SimplifyOutput
+{
+	u32 group_count = 0;
+	u32 triangle_count = 0;
+	u32* tri = nullptr;              // simplified triangles (global vertex ids), group-major
+	u32* group_tri_offset = nullptr; // group_count + 1
+	float* group_error = nullptr;    // absolute error per group (meshopt_SimplifyErrorAbsolute)
+};
+struct SimplifyStats
+{
+	u32 passes = 0;
+	u32 rounds = 0;
+	u32 max_rounds = 0;
+};
+extern SimplifyStats g_simplify_stats;
+// One meshopt_simplifyWithAttributes(Sparse|ErrorAbsolute|Permissive) per group, all groups batched. gtri holds each
+// group's merged index list back to back; locks is the per-vertex lock byte array of the level.
+SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host, u32 group_count, const DeviceMesh& mesh, const u32* global_remap, const u8* locks, const Config& config, Workspace& ws);
+
 } // namespace clodb

@@ -44,17 +44,42 @@ static inline void iota(u32* p, size_t n)
 	LAUNCH(k_iota, n, p, n);
 }
 
+struct OpAddU32
+{
+	HOSTDEVFN u32 identity()
+	{
+		return 0;
+	}
+	HOSTDEVFN u32 apply(u32 a, u32 b)
+	{
+		return a + b;
+	}
+};
+
+struct OpMaxU64
+{
+	HOSTDEVFN u64 identity()
+	{
+		return 0;
+	}
+	HOSTDEVFN u64 apply(u64 a, u64 b)
+	{
+		return a > b ? a : b;
+	}
+};
+
 #ifdef CLODB_EMU
 // ------------------------------------------------------------------------------------------------------- emulation
-static inline void exclusive_scan_u32(const u32* in, u32* out, size_t n, u32* total, Arena&)
+template <typename T, typename Op>
+static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena&)
 {
 	g_launches += 3;
-	u32 sum = 0;
+	T sum = Op::identity();
 	for (size_t i = 0; i < n; ++i)
 	{
-		u32 v = in[i];
+		T v = in[i];
 		out[i] = sum;
-		sum += v;
+		sum = Op::apply(sum, v);
 	}
 	if (total)
 		*total = sum;
@@ -88,150 +113,144 @@ static const int SCAN_THREADS = 256;
 static const int SCAN_ITEMS = 8;
 static const int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-DEVFN u32 warp_inclusive_scan(u32 v, int lane)
+template <typename T>
+DEVFN T shfl_up_any(T v, int d)
+{
+	return __shfl_up_sync(0xffffffffu, v, d);
+}
+
+template <typename T, typename Op>
+DEVFN T warp_inclusive_scan(T v, int lane)
 {
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
 	{
-		u32 t = __shfl_up_sync(0xffffffffu, v, d);
+		T t = shfl_up_any(v, d);
 		if (lane >= d)
-			v += t;
+			v = Op::apply(t, v);
 	}
 	return v;
 }
 
-// exclusive scan of one value per thread across a 256-thread block; returns exclusive prefix, *block_total = sum
-DEVFN u32 block_exclusive_scan(u32 v, u32* block_total, u32* smem /* >= 9 */)
+// exclusive scan of one value per thread across the CTA; smem must hold 34 values
+template <typename T, typename Op>
+DEVFN T block_exclusive_scan(T v, T* block_total, T* smem)
 {
 	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	u32 inc = warp_inclusive_scan(v, lane);
+	int nwarps = blockDim.x >> 5;
+	T inc = warp_inclusive_scan<T, Op>(v, lane);
+	T ex = shfl_up_any(inc, 1);
+	if (lane == 0)
+		ex = Op::identity();
 	if (lane == 31)
 		smem[warp] = inc;
 	__syncthreads();
 	if (warp == 0)
 	{
-		u32 w = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0;
-		u32 winc = warp_inclusive_scan(w, lane);
-		if (lane < (int)(blockDim.x >> 5))
-			smem[lane] = winc - w;
+		T w = lane < nwarps ? smem[lane] : Op::identity();
+		T winc = warp_inclusive_scan<T, Op>(w, lane);
+		T wex = shfl_up_any(winc, 1);
+		if (lane == 0)
+			wex = Op::identity();
+		if (lane < nwarps)
+			smem[lane] = wex;
 		if (lane == 31)
-			smem[32] = winc;
+			smem[33] = winc;
 	}
 	__syncthreads();
-	u32 result = smem[warp] + inc - v;
-	*block_total = smem[32];
+	T result = Op::apply(smem[warp], ex);
+	*block_total = smem[33];
 	__syncthreads();
 	return result;
 }
 
-static __global__ void k_scan_reduce(const u32* __restrict__ in, u32* __restrict__ block_sums, size_t n)
+template <typename T, typename Op>
+__global__ void k_scan_reduce(const T* __restrict__ in, T* __restrict__ block_sums, size_t n)
 {
-	__shared__ u32 smem[33];
+	__shared__ T smem[34];
 	size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
-	u32 sum = 0;
-	if (base + SCAN_ITEMS <= n)
-	{
-		const uint4* p = reinterpret_cast<const uint4*>(in + base);
-		uint4 a = p[0], b = p[1];
-		sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-	}
-	else
-	{
-		for (int k = 0; k < SCAN_ITEMS; ++k)
-			if (base + k < n)
-				sum += in[base + k];
-	}
-	u32 total;
-	block_exclusive_scan(sum, &total, smem);
+	T sum = Op::identity();
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+		if (base + k < n)
+			sum = Op::apply(sum, in[base + k]);
+	T total;
+	block_exclusive_scan<T, Op>(sum, &total, smem);
 	if (threadIdx.x == 0)
 		block_sums[blockIdx.x] = total;
 }
 
 // single-CTA scan of the per-tile sums (1024 threads, looping with a running carry)
-static __global__ void k_scan_blocksums(u32* __restrict__ block_sums, size_t nblocks, u32* __restrict__ total_out)
+template <typename T, typename Op>
+__global__ void k_scan_blocksums(T* __restrict__ block_sums, size_t nblocks, T* __restrict__ total_out)
 {
-	__shared__ u32 smem[33];
-	__shared__ u32 carry_s;
+	__shared__ T smem[34];
+	__shared__ T carry_s;
 	if (threadIdx.x == 0)
-		carry_s = 0;
+		carry_s = Op::identity();
 	__syncthreads();
 	for (size_t base = 0; base < nblocks; base += blockDim.x)
 	{
 		size_t i = base + threadIdx.x;
-		u32 v = i < nblocks ? block_sums[i] : 0;
-		u32 total;
-		u32 ex = block_exclusive_scan(v, &total, smem);
-		u32 carry = carry_s;
+		T v = i < nblocks ? block_sums[i] : Op::identity();
+		T total;
+		T ex = block_exclusive_scan<T, Op>(v, &total, smem);
+		T carry = carry_s;
 		if (i < nblocks)
-			block_sums[i] = carry + ex;
+			block_sums[i] = Op::apply(carry, ex);
 		__syncthreads();
 		if (threadIdx.x == 0)
-			carry_s = carry + total;
+			carry_s = Op::apply(carry, total);
 		__syncthreads();
 	}
 	if (threadIdx.x == 0 && total_out)
 		*total_out = carry_s;
 }
 
-static __global__ void k_scan_apply(const u32* __restrict__ in, u32* __restrict__ out, const u32* __restrict__ block_sums, size_t n)
+template <typename T, typename Op>
+__global__ void k_scan_apply(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ block_sums, size_t n)
 {
-	__shared__ u32 smem[33];
+	__shared__ T smem[34];
 	size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
-	u32 v[SCAN_ITEMS];
-	bool full = base + SCAN_ITEMS <= n;
-	if (full)
-	{
-		const uint4* p = reinterpret_cast<const uint4*>(in + base);
-		uint4 a = p[0], b = p[1];
-		v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
-	}
-	else
-	{
-		for (int k = 0; k < SCAN_ITEMS; ++k)
-			v[k] = base + k < n ? in[base + k] : 0;
-	}
-	u32 sum = 0;
-#pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k)
-		sum += v[k];
-	u32 total;
-	u32 run = block_exclusive_scan(sum, &total, smem) + block_sums[blockIdx.x];
+	T v[SCAN_ITEMS];
+	T sum = Op::identity();
 #pragma unroll
 	for (int k = 0; k < SCAN_ITEMS; ++k)
 	{
-		u32 t = v[k];
+		v[k] = base + k < n ? in[base + k] : Op::identity();
+		sum = Op::apply(sum, v[k]);
+	}
+	T total;
+	T run = Op::apply(block_sums[blockIdx.x], block_exclusive_scan<T, Op>(sum, &total, smem));
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+	{
+		T t = v[k];
 		v[k] = run;
-		run += t;
+		run = Op::apply(run, t);
 	}
-	if (full)
-	{
-		uint4* p = reinterpret_cast<uint4*>(out + base);
-		p[0] = make_uint4(v[0], v[1], v[2], v[3]);
-		p[1] = make_uint4(v[4], v[5], v[6], v[7]);
-	}
-	else
-	{
-		for (int k = 0; k < SCAN_ITEMS; ++k)
-			if (base + k < n)
-				out[base + k] = v[k];
-	}
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+		if (base + k < n)
+			out[base + k] = v[k];
 }
 
-// out[i] = sum(in[0..i)), in-place allowed; optional device-side total
-static inline void exclusive_scan_u32(const u32* in, u32* out, size_t n, u32* total, Arena& arena)
+// out[i] = op(in[0..i)), in-place allowed; optional device-side total
+template <typename T, typename Op>
+static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena& arena)
 {
 	if (n == 0)
 	{
 		if (total)
-			dev_memset(total, 0, sizeof(u32));
+			dev_memset(total, 0, sizeof(T));
 		return;
 	}
 	ArenaScope scope(arena);
 	size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-	u32* block_sums = arena.alloc<u32>(nblocks);
-	LAUNCH_GRID(k_scan_reduce, nblocks, SCAN_THREADS, in, block_sums, n);
-	LAUNCH_GRID(k_scan_blocksums, 1, 1024, block_sums, nblocks, total);
-	LAUNCH_GRID(k_scan_apply, nblocks, SCAN_THREADS, in, out, block_sums, n);
+	T* block_sums = arena.alloc<T>(nblocks);
+	LAUNCH_GRID((k_scan_reduce<T, Op>), nblocks, SCAN_THREADS, in, block_sums, n);
+	LAUNCH_GRID((k_scan_blocksums<T, Op>), 1, 1024, block_sums, nblocks, total);
+	LAUNCH_GRID((k_scan_apply<T, Op>), nblocks, SCAN_THREADS, in, out, block_sums, n);
 }
 
 // ---- radix sort ------------------------------------------------------------------------------------------------
@@ -343,7 +362,7 @@ static inline void radix_sort_pairs(K* keys, K* keys_tmp, u32* vals, u32* vals_t
 	for (int shift = bit_lo; shift < bit_hi; shift += 8)
 	{
 		LAUNCH_GRID(k_rs_hist<K>, nblocks, RS_THREADS, src, counts, n, shift, nblocks);
-		exclusive_scan_u32(counts, counts, size_t(256) * nblocks, nullptr, arena);
+		exclusive_scan<u32, OpAddU32>(counts, counts, size_t(256) * nblocks, nullptr, arena);
 		LAUNCH_GRID(k_rs_scatter<K>, nblocks, RS_THREADS, src, dst, vsrc, vdst, counts, n, shift, nblocks);
 		K* t = src;
 		src = dst;
@@ -360,6 +379,11 @@ static inline void radix_sort_pairs(K* keys, K* keys_tmp, u32* vals, u32* vals_t
 	}
 }
 #endif
+
+static inline void exclusive_scan_u32(const u32* in, u32* out, size_t n, u32* total, Arena& arena)
+{
+	exclusive_scan<u32, OpAddU32>(in, out, n, total, arena);
+}
 
 static inline int bits_for(u64 max_value)
 {

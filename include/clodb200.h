@@ -82,6 +82,24 @@ int clodb200_clusterize(const clodb200_config* config, const unsigned int* indic
 int clodb200_computeClusterBounds(const unsigned int* indices, const unsigned int* cluster_index_counts, size_t cluster_count,
     const float* positions, size_t vertex_count, size_t positions_stride, float* out_bounds4);
 
+/* clod::lockBoundary (clusterlod.h:512-559) for one DAG level. indices holds the merged index lists of all groups back
+ * to back, group_index_offsets[group_count + 1] delimits them. locks[vertex_count] is updated in place: bit0 = position
+ * shared by >= 2 groups, bit1 (protect) kept, vertex_lock (optional) ORed in. remap = position remap of the mesh. */
+int clodb200_lockBoundary(unsigned char* locks, const unsigned int* indices, const unsigned int* group_index_offsets, size_t group_count,
+    const unsigned int* remap, const unsigned char* vertex_lock, size_t vertex_count);
+
+/* clod::simplify (clusterlod.h:601-659: meshopt_simplifyWithAttributes with Sparse|ErrorAbsolute|Permissive) for every
+ * group of a DAG level in one batched call. Each group g is simplified towards size_t(T_g * simplify_ratio) triangles.
+ * out_indices (capacity = total index count) receives the simplified lists back to back, out_group_index_counts[g] and
+ * out_group_errors[g] the per-group result size and absolute error. attributes may be NULL (attribute_count 0). */
+int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* indices, const unsigned int* group_index_offsets, size_t group_count,
+    const float* positions, size_t vertex_count, size_t positions_stride,
+    const float* attributes, size_t attributes_stride, const float* attribute_weights, size_t attribute_count,
+    const unsigned char* locks, unsigned int* out_indices, unsigned int* out_group_index_counts, float* out_group_errors);
+
+/* Diagnostics of the last clodb200_simplifyGroups / build on this process: {passes, wavefront rounds, max rounds in a pass}. */
+void clodb200_simplifyStats(unsigned int out3[3]);
+
 #ifdef __cplusplus
 }
 #endif
