@@ -48,6 +48,57 @@ class Config(C.Structure):
     ]
 
 
+class MeshDesc(C.Structure):
+    """struct clodb200_mesh == struct clodMesh (clusterlod.h:73-99)."""
+
+    _fields_ = [
+        ("indices", C.c_void_p),
+        ("index_count", C.c_size_t),
+        ("vertex_count", C.c_size_t),
+        ("vertex_positions", C.c_void_p),
+        ("vertex_positions_stride", C.c_size_t),
+        ("vertex_attributes", C.c_void_p),
+        ("vertex_attributes_stride", C.c_size_t),
+        ("vertex_lock", C.c_void_p),
+        ("attribute_weights", C.c_void_p),
+        ("attribute_count", C.c_size_t),
+        ("attribute_protect_mask", C.c_uint),
+    ]
+
+
+class Bounds(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("error", C.c_float)]
+
+
+class Cluster(C.Structure):
+    _fields_ = [("refined", C.c_int), ("bounds", Bounds), ("indices", C.POINTER(C.c_uint)), ("index_count", C.c_size_t), ("vertex_count", C.c_size_t)]
+
+
+class Group(C.Structure):
+    _fields_ = [("depth", C.c_int), ("simplified", Bounds)]
+
+
+OUTPUT_EX = C.CFUNCTYPE(C.c_int, C.c_void_p, Group, C.POINTER(Cluster), C.c_size_t, C.c_size_t, C.c_uint)
+
+_RECORD_DTYPES = {
+    "group_depth": np.int32, "group_simplified": np.float32, "group_cluster_offsets": np.uint32, "cluster_refined": np.int32,
+    "cluster_bounds": np.float32, "cluster_vertex_count": np.uint32, "cluster_index_offsets": np.uint64, "cluster_indices": np.uint32,
+    "level_triangles": np.uint32, "level_clusters": np.uint32, "level_groups": np.uint32, "stats": np.uint64,
+}
+
+
+class DagRecord:
+    """The complete output callback stream of one DAG build, as numpy arrays."""
+
+    def __init__(self, arrays):
+        self.__dict__.update(arrays)
+        self.group_simplified = self.group_simplified.reshape(-1, 5)
+        self.cluster_bounds = self.cluster_bounds.reshape(-1, 5)
+        st = self.stats
+        self.total_clusters, self.levels, self.groups = int(st[0]), int(st[1]), int(st[2])
+        self.simplify_passes, self.simplify_rounds, self.launches = int(st[5]), int(st[6]), int(st[7])
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -71,6 +122,17 @@ class ClodLib:
         L.clodb200_lockBoundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
         L.clodb200_simplifyGroups.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.clodb200_simplifyStats.argtypes = [C.c_void_p]
+        L.clodb200_buildRecorded.restype = C.c_void_p
+        L.clodb200_buildRecorded.argtypes = [Config, MeshDesc]
+        L.clodb200_meshUpload.restype = C.c_void_p
+        L.clodb200_meshUpload.argtypes = [MeshDesc]
+        L.clodb200_meshFree.argtypes = [C.c_void_p]
+        L.clodb200_meshBuildRecorded.restype = C.c_void_p
+        L.clodb200_meshBuildRecorded.argtypes = [Config, C.c_void_p, C.c_int]
+        L.clodb200_recordGet.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.clodb200_recordFree.argtypes = [C.c_void_p]
+        L.clodb200_buildEx.restype = C.c_size_t
+        L.clodb200_buildEx.argtypes = [Config, MeshDesc, C.c_void_p, OUTPUT_EX, C.c_void_p]
         self._check(L.clodb200_init(device))
 
     def _check(self, status: int):
@@ -148,6 +210,76 @@ class ClodLib:
         out_offs = np.zeros(G + 1, dtype=np.uint32)
         np.cumsum(counts, out=out_offs[1:])
         return out[: out_offs[-1]].copy(), out_offs, errors
+
+    # ---- DAG build ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def mesh_desc(positions, indices, attributes=None, attribute_weights=None, protect_mask=0, vertex_lock=None, positions_stride=None, attributes_stride=None, vertex_count=None):
+        """Builds a clodb200_mesh over numpy arrays; returns (desc, keepalive)."""
+        if positions_stride is None:
+            positions = np.ascontiguousarray(positions, dtype=np.float32)
+            vertex_count, positions_stride = positions.shape[0], positions.shape[1] * 4
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        d = MeshDesc()
+        d.indices, d.index_count, d.vertex_count = _ptr(indices), indices.size, vertex_count
+        d.vertex_positions, d.vertex_positions_stride = _ptr(positions), positions_stride
+        keep = [positions, indices]
+        if attributes is not None:
+            if attributes_stride is None:
+                attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+                attributes_stride = attributes.shape[1] * 4
+            attribute_weights = np.ascontiguousarray(attribute_weights, dtype=np.float32)
+            d.vertex_attributes, d.vertex_attributes_stride = _ptr(attributes), attributes_stride
+            d.attribute_weights, d.attribute_count = _ptr(attribute_weights), attribute_weights.size
+            d.attribute_protect_mask = protect_mask
+            keep += [attributes, attribute_weights]
+        if vertex_lock is not None:
+            vertex_lock = np.ascontiguousarray(vertex_lock, dtype=np.uint8)
+            d.vertex_lock = _ptr(vertex_lock)
+            keep.append(vertex_lock)
+        return d, keep
+
+    def _record(self, handle) -> DagRecord:
+        if not handle:
+            raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200 build failed")
+        arrays = {}
+        for name, dtype in _RECORD_DTYPES.items():
+            ptr, size = C.c_void_p(), C.c_size_t()
+            self._lib.clodb200_recordGet(handle, name.encode(), C.byref(ptr), C.byref(size))
+            arrays[name] = np.frombuffer(C.string_at(ptr, size.value), dtype=dtype).copy() if size.value else np.zeros(0, dtype)
+        self._lib.clodb200_recordFree(handle)
+        return DagRecord(arrays)
+
+    def build_dag(self, positions, indices, attributes=None, attribute_weights=None, protect_mask=0, config: Config | None = None, **kw) -> DagRecord:
+        """clodBuildEx-equivalent on host arrays (upload + build + read-back), recording the callback stream."""
+        desc, keep = self.mesh_desc(positions, indices, attributes, attribute_weights, protect_mask, **kw)
+        return self._record(self._lib.clodb200_buildRecorded(config or self.builder_config(), desc))
+
+    def upload_mesh(self, positions, indices, attributes=None, attribute_weights=None, protect_mask=0, **kw):
+        desc, keep = self.mesh_desc(positions, indices, attributes, attribute_weights, protect_mask, **kw)
+        h = self._lib.clodb200_meshUpload(desc)
+        if not h:
+            raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200 mesh upload failed")
+        return h
+
+    def free_mesh(self, handle):
+        self._lib.clodb200_meshFree(handle)
+
+    def build_dag_resident(self, mesh_handle, config: Config | None = None, keep_indices: bool = True) -> DagRecord:
+        return self._record(self._lib.clodb200_meshBuildRecorded(config or self.builder_config(), mesh_handle, 1 if keep_indices else 0))
+
+    def build_ex(self, positions, indices, callback, attributes=None, attribute_weights=None, protect_mask=0, config: Config | None = None) -> int:
+        """clodBuildEx with a Python callback(group: Group, clusters: [Cluster], task_index) -> refined id."""
+        desc, keep = self.mesh_desc(positions, indices, attributes, attribute_weights, protect_mask)
+
+        def tramp(ctx, group, clusters, count, task_index, thread_index):
+            return int(callback(group, [clusters[i] for i in range(count)], task_index))
+
+        cb = OUTPUT_EX(tramp)
+        n = self._lib.clodb200_buildEx(config or self.builder_config(), desc, None, cb, None)
+        err = self._lib.clodb200_last_error().decode()
+        if n == 0 and err:
+            raise ClodbError(err)
+        return n
 
     def simplify_stats(self):
         a = (C.c_uint * 3)()

@@ -1,6 +1,9 @@
 // clodb200 C ABI (include/clodb200.h): argument checking, host<->device staging, error translation.
 #include "../../include/clodb200.h"
 #include "clodb.h"
+#include "dag.h"
+
+#include <map>
 
 #include <mutex>
 
@@ -93,6 +96,55 @@ int guarded(F&& body)
 	}
 }
 } // namespace
+
+struct clodb200_record
+{
+	std::map<std::string, std::vector<unsigned char> > blobs;
+
+	template <typename T>
+	void append(const char* name, const T* data, size_t count)
+	{
+		std::vector<unsigned char>& b = blobs[name];
+		size_t old = b.size();
+		b.resize(old + count * sizeof(T));
+		if (count)
+			memcpy(b.data() + old, data, count * sizeof(T));
+	}
+	template <typename T>
+	void push(const char* name, T v)
+	{
+		append(name, &v, 1);
+	}
+};
+
+struct RecordSink : DagSink
+{
+	clodb200_record* rec;
+	bool keep_indices = true;
+	int next_group = 0;
+	u32 cluster_total = 0;
+	u64 index_total = 0;
+
+	int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t) override
+	{
+		rec->push<int>("group_depth", group.depth);
+		rec->append<float>("group_simplified", group.simplified, 5);
+		for (size_t i = 0; i < cluster_count; ++i)
+		{
+			const DagCluster& c = clusters[i];
+			rec->push<int>("cluster_refined", c.refined);
+			rec->append<float>("cluster_bounds", c.bounds, 5);
+			rec->push<u32>("cluster_vertex_count", u32(c.vertex_count));
+			if (keep_indices)
+				rec->append<unsigned int>("cluster_indices", c.indices, c.index_count);
+			index_total += c.index_count;
+			rec->push<u64>("cluster_index_offsets", index_total);
+		}
+		cluster_total += u32(cluster_count);
+		rec->push<u32>("group_cluster_offsets", cluster_total);
+		return next_group++;
+	}
+};
 
 extern "C"
 {
@@ -354,6 +406,293 @@ int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* i
 		dev_d2h(out_group_errors, so.group_error, group_count * 4);
 		return CLODB200_OK;
 	});
+}
+
+struct clodb200_device_mesh
+{
+	DeviceMesh mesh;
+	u32* indices = nullptr;
+	size_t index_count = 0;
+	std::vector<void*> allocations;
+};
+
+static bool validate_mesh(const clodb200_mesh& mesh)
+{
+	// clusterlod.h:796-816
+	const bool missingIndices = mesh.index_count > 0 && mesh.indices == NULL;
+	const bool missingPositions = mesh.vertex_count > 0 && mesh.vertex_positions == NULL;
+	const bool missingAttributes = mesh.attribute_count > 0 && mesh.vertex_attributes == NULL;
+	const bool emptyGeometry = mesh.index_count == 0 || mesh.vertex_count == 0;
+	const bool invalidPositionStride = mesh.vertex_positions_stride < sizeof(float) * 3;
+	const bool invalidAttributeStride = mesh.attribute_count > 0 && mesh.vertex_attributes_stride < mesh.attribute_count * sizeof(float);
+	if (emptyGeometry || missingIndices || missingPositions || missingAttributes || invalidPositionStride || invalidAttributeStride)
+	{
+		fprintf(stderr,
+		    "clusterlod: skipping mesh with invalid or empty geometry (index_count=%zu, vertex_count=%zu, indices=%p, positions=%p, position_stride=%zu, attribute_count=%zu, attributes=%p, attribute_stride=%zu)\n",
+		    mesh.index_count, mesh.vertex_count, static_cast<const void*>(mesh.indices), static_cast<const void*>(mesh.vertex_positions), mesh.vertex_positions_stride,
+		    mesh.attribute_count, static_cast<const void*>(mesh.vertex_attributes), mesh.vertex_attributes_stride);
+		return false;
+	}
+	return true;
+}
+
+static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
+{
+	if (mesh.index_count % 3 || mesh.vertex_positions_stride % 4 || mesh.vertex_attributes_stride % 4 || mesh.attribute_count > 32)
+		throw Error("clodb200: index count must be a multiple of 3, strides multiples of 4, at most 32 attributes");
+	for (size_t i = 0; i < mesh.index_count; ++i)
+		if (mesh.indices[i] >= mesh.vertex_count)
+			throw Error("clodb200: index out of range");
+	clodb200_device_mesh* dm = new clodb200_device_mesh();
+	try
+	{
+		size_t V = mesh.vertex_count;
+		float* dpos = static_cast<float*>(dev_malloc(V * 12));
+		dm->allocations.push_back(dpos);
+		if (mesh.vertex_positions_stride == 12)
+			dev_h2d(dpos, mesh.vertex_positions, V * 12);
+		else
+		{
+			std::vector<float> packed(V * 3);
+			size_t stride = mesh.vertex_positions_stride / 4;
+			for (size_t i = 0; i < V; ++i)
+				for (int k = 0; k < 3; ++k)
+					packed[i * 3 + k] = mesh.vertex_positions[i * stride + k];
+			dev_h2d(dpos, packed.data(), V * 12);
+		}
+		dm->mesh.positions = dpos;
+		dm->mesh.vertex_count = V;
+		size_t astride = mesh.vertex_attributes_stride / 4;
+		if (mesh.vertex_attributes && astride)
+		{
+			float* dattr = static_cast<float*>(dev_malloc(V * astride * 4));
+			dm->allocations.push_back(dattr);
+			dev_h2d(dattr, mesh.vertex_attributes, V * astride * 4);
+			dm->mesh.attributes = dattr;
+			dm->mesh.attribute_stride = u32(astride);
+			dm->mesh.attribute_count = u32(mesh.attribute_count);
+			for (size_t i = 0; i < mesh.attribute_count; ++i)
+				dm->mesh.attribute_weights[i] = mesh.attribute_weights[i];
+			dm->mesh.attribute_protect_mask = mesh.attribute_protect_mask;
+		}
+		if (mesh.vertex_lock)
+		{
+			u8* dl = static_cast<u8*>(dev_malloc(V));
+			dm->allocations.push_back(dl);
+			dev_h2d(dl, mesh.vertex_lock, V);
+			dm->mesh.vertex_lock = dl;
+		}
+		dm->indices = static_cast<u32*>(dev_malloc(mesh.index_count * 4));
+		dm->allocations.push_back(dm->indices);
+		dev_h2d(dm->indices, mesh.indices, mesh.index_count * 4);
+		dm->index_count = mesh.index_count;
+	}
+	catch (...)
+	{
+		for (void* p : dm->allocations)
+			dev_free(p);
+		delete dm;
+		throw;
+	}
+	return dm;
+}
+
+static void free_mesh_locked(clodb200_device_mesh* dm)
+{
+	if (!dm)
+		return;
+	for (void* p : dm->allocations)
+		dev_free(p);
+	delete dm;
+}
+
+struct CallbackSink : DagSink
+{
+	void* context;
+	clodb200_outputEx callback_ex;
+	clodb200_output callback;
+
+	int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t task_index) override
+	{
+		static_assert(sizeof(DagCluster) == sizeof(clodb200_cluster) && sizeof(DagGroup) == sizeof(clodb200_group), "layout");
+		clodb200_group g;
+		memcpy(&g, &group, sizeof(g));
+		const clodb200_cluster* c = reinterpret_cast<const clodb200_cluster*>(clusters);
+		if (callback_ex)
+			return callback_ex(context, g, c, cluster_count, task_index, 0);
+		if (callback)
+			return callback(context, g, c, cluster_count);
+		return -1;
+	}
+};
+
+static BuildStats g_last_build_stats;
+
+static size_t build_locked(const clodb200_config& config, const clodb200_device_mesh* dm, DagSink& sink)
+{
+	size_t T = dm->index_count / 3;
+	size_t V = dm->mesh.vertex_count;
+	size_t scale_temp = 640, scale_persist = 96;
+	if (const char* e = getenv("CLODB200_TEMP_BYTES_PER_TRI"))
+		scale_temp = size_t(atoll(e));
+	ensure_workspace(T * scale_persist + V * 32 + (64u << 20), T * scale_temp + V * 16 + (64u << 20));
+	return build_dag(to_config(&config), dm->mesh, dm->indices, dm->index_count, g_ws, sink, g_last_build_stats);
+}
+
+size_t clodb200_meshBuildEx(clodb200_config config, const clodb200_device_mesh* mesh, void* output_context, clodb200_outputEx output_callback)
+{
+	size_t result = 0;
+	int status = guarded([&]() -> int {
+		if (!mesh)
+			return fail(CLODB200_ERR_INVALID, "clodb200_meshBuildEx: null mesh");
+		CallbackSink sink;
+		sink.context = output_context;
+		sink.callback_ex = output_callback;
+		sink.callback = nullptr;
+		t_last_error.clear();
+		result = build_locked(config, mesh, sink);
+		return CLODB200_OK;
+	});
+	return status == CLODB200_OK ? result : 0;
+}
+
+clodb200_device_mesh* clodb200_meshUpload(clodb200_mesh mesh)
+{
+	clodb200_device_mesh* dm = nullptr;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!validate_mesh(mesh))
+			return fail(CLODB200_ERR_INVALID, "clodb200: invalid or empty geometry");
+		dm = upload_mesh_locked(mesh);
+		return CLODB200_OK;
+	});
+	return dm;
+}
+
+void clodb200_meshFree(clodb200_device_mesh* mesh)
+{
+	guarded([&]() -> int {
+		free_mesh_locked(mesh);
+		return CLODB200_OK;
+	});
+}
+
+static size_t build_host(clodb200_config config, clodb200_mesh mesh, void* output_context, clodb200_outputEx cb_ex, clodb200_output cb)
+{
+	size_t result = 0;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!validate_mesh(mesh))
+			return CLODB200_OK; // the reference returns 0 without failing
+		clodb200_device_mesh* dm = upload_mesh_locked(mesh);
+		try
+		{
+			CallbackSink sink;
+			sink.context = output_context;
+			sink.callback_ex = cb_ex;
+			sink.callback = cb;
+			result = build_locked(config, dm, sink);
+		}
+		catch (...)
+		{
+			free_mesh_locked(dm);
+			throw;
+		}
+		free_mesh_locked(dm);
+		return CLODB200_OK;
+	});
+	return result;
+}
+
+size_t clodb200_build(clodb200_config config, clodb200_mesh mesh, void* output_context, clodb200_output output_callback)
+{
+	return build_host(config, mesh, output_context, nullptr, output_callback);
+}
+
+size_t clodb200_buildEx(clodb200_config config, clodb200_mesh mesh, void* output_context, clodb200_outputEx output_callback, const void*)
+{
+	return build_host(config, mesh, output_context, output_callback, nullptr);
+}
+
+static clodb200_record* record_build(const clodb200_config& config, const clodb200_device_mesh* dm, bool keep_indices)
+{
+	clodb200_record* rec = new clodb200_record();
+	try
+	{
+		RecordSink sink;
+		sink.rec = rec;
+		sink.keep_indices = keep_indices;
+		rec->push<u32>("group_cluster_offsets", 0);
+		rec->push<u64>("cluster_index_offsets", 0);
+		size_t clusters = build_locked(config, dm, sink);
+		const BuildStats& st = g_last_build_stats;
+		rec->append<u32>("level_triangles", st.level_triangles.data(), st.level_triangles.size());
+		rec->append<u32>("level_clusters", st.level_clusters.data(), st.level_clusters.size());
+		rec->append<u32>("level_groups", st.level_groups.data(), st.level_groups.size());
+		u64 stats[8] = {u64(clusters), st.levels, st.groups, st.simplified_triangles, st.d2h_bytes, st.simplify_passes, st.simplify_rounds, g_launches};
+		rec->append<u64>("stats", stats, 8);
+	}
+	catch (...)
+	{
+		delete rec;
+		throw;
+	}
+	return rec;
+}
+
+clodb200_record* clodb200_meshBuildRecorded(clodb200_config config, const clodb200_device_mesh* mesh, int keep_indices)
+{
+	clodb200_record* rec = nullptr;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!mesh)
+			return fail(CLODB200_ERR_INVALID, "clodb200_meshBuildRecorded: null mesh");
+		rec = record_build(config, mesh, keep_indices != 0);
+		return CLODB200_OK;
+	});
+	return rec;
+}
+
+clodb200_record* clodb200_buildRecorded(clodb200_config config, clodb200_mesh mesh)
+{
+	clodb200_record* rec = nullptr;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!validate_mesh(mesh))
+			return fail(CLODB200_ERR_INVALID, "clodb200: invalid or empty geometry");
+		clodb200_device_mesh* dm = upload_mesh_locked(mesh);
+		try
+		{
+			rec = record_build(config, dm, true);
+		}
+		catch (...)
+		{
+			free_mesh_locked(dm);
+			throw;
+		}
+		free_mesh_locked(dm);
+		return CLODB200_OK;
+	});
+	return rec;
+}
+
+int clodb200_recordGet(const clodb200_record* record, const char* name, const void** out_ptr, size_t* out_bytes)
+{
+	*out_ptr = nullptr;
+	*out_bytes = 0;
+	if (!record)
+		return 0;
+	auto it = record->blobs.find(name);
+	if (it == record->blobs.end())
+		return 0;
+	*out_ptr = it->second.data();
+	*out_bytes = it->second.size();
+	return 1;
+}
+
+void clodb200_recordFree(clodb200_record* record)
+{
+	delete record;
 }
 
 void clodb200_simplifyStats(unsigned int out3[3])

@@ -76,6 +76,19 @@ void cluster_bounds(const u32* tri, const u32* cluster_tri_offset, u32 cluster_c
 // sphere-of-spheres per group as clod::boundsMerge (clusterlod.h:283-303): out5 = {c, r, max error}
 void group_bounds_merge(const float* cluster_bounds5, const u32* group_cluster_offset, const u32* group_clusters, u32 group_count, float* out5);
 
+// ---- S4: grouping (partition.cu) ------------------------------------------------------------------------------------
+struct GroupSet
+{
+	u32 group_count = 0;
+	u32 cluster_count = 0;
+	u32* group_clusters = nullptr;       // cluster ids, group-major (ascending cluster id inside a group unless cap-split)
+	u32* group_cluster_offset = nullptr; // group_count + 1
+	std::vector<u32> group_cluster_offset_host;
+	u32 merge_rounds = 0;
+};
+// clod::partition (clusterlod.h:350-510) for the pending clusters of one level (all K clusters of the ClusterSet)
+GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 cluster_count, const int* cluster_refined, const float* cluster_bounds5, const u32* remap, const float* positions, size_t vertex_count, const Config& config, Workspace& ws);
+
 // ---- S5: group assembly + boundary locks (groups.cu) --------------------------------------------------------------
 // Gathers the triangles of each group (clusters listed group-major in group_clusters) into one contiguous run per group,
 // as runIterationTask's merge (clusterlod.h:708-711). Returns the per-group triangle offsets (host) in out_offsets.

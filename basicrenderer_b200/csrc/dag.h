@@ -1,0 +1,47 @@
+// DAG driver interface (dag.cu).
+#pragma once
+
+#include "clodb.h"
+
+namespace clodb
+{
+
+// Layout-compatible with clodCluster / clodGroup (clusterlod.h:105-141) so the C ABI can hand them to the reference's
+// own callback type without repacking.
+struct DagCluster
+{
+	int refined;
+	float bounds[5]; // center xyz, radius, error
+	const unsigned int* indices;
+	size_t index_count;
+	size_t vertex_count;
+};
+
+struct DagGroup
+{
+	int depth;
+	float simplified[5];
+};
+
+struct DagSink
+{
+	virtual ~DagSink() {}
+	// returns the id stored as `refined` for clusters produced from this group
+	virtual int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t task_index) = 0;
+};
+
+struct BuildStats
+{
+	u32 levels = 0;
+	u32 groups = 0;
+	size_t total_clusters = 0;
+	size_t simplified_triangles = 0;
+	size_t d2h_bytes = 0;
+	u32 simplify_passes = 0;
+	u32 simplify_rounds = 0;
+	std::vector<u32> level_triangles, level_clusters, level_groups;
+};
+
+size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indices_dev, size_t index_count, Workspace& ws, DagSink& sink, BuildStats& stats);
+
+} // namespace clodb

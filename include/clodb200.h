@@ -97,6 +97,74 @@ int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* i
     const float* attributes, size_t attributes_stride, const float* attribute_weights, size_t attribute_count,
     const unsigned char* locks, unsigned int* out_indices, unsigned int* out_group_index_counts, float* out_group_errors);
 
+/* ---- DAG build: drop-in for clodBuild / clodBuildEx (clusterlod.h:159-184) -------------------------------------- */
+
+/* Same layout as struct clodMesh, clusterlod.h:73-99. Pointers are host pointers, borrowed for the duration of the call. */
+typedef struct clodb200_mesh
+{
+	const unsigned int* indices;
+	size_t index_count;
+	size_t vertex_count;
+	const float* vertex_positions;
+	size_t vertex_positions_stride;
+	const float* vertex_attributes;
+	size_t vertex_attributes_stride;
+	const unsigned char* vertex_lock;
+	const float* attribute_weights;
+	size_t attribute_count;
+	unsigned int attribute_protect_mask;
+} clodb200_mesh;
+
+/* Same layouts as clodBounds / clodCluster / clodGroup, clusterlod.h:105-141. */
+typedef struct clodb200_bounds
+{
+	float center[3];
+	float radius;
+	float error;
+} clodb200_bounds;
+
+typedef struct clodb200_cluster
+{
+	int refined;
+	clodb200_bounds bounds;
+	const unsigned int* indices; /* valid only during the callback, like the reference's */
+	size_t index_count;
+	size_t vertex_count;
+} clodb200_cluster;
+
+typedef struct clodb200_group
+{
+	int depth;
+	clodb200_bounds simplified;
+} clodb200_group;
+
+/* Same signatures as clodOutput / clodOutputEx (clusterlod.h:146-148). Called serially on the calling thread, depth by
+ * depth, groups in partition order; the return value becomes clodb200_cluster::refined of the clusters simplified from
+ * that group. thread_index is always 0 (the per-group iteration tasks run on the GPU). */
+typedef int (*clodb200_output)(void* output_context, clodb200_group group, const clodb200_cluster* clusters, size_t cluster_count);
+typedef int (*clodb200_outputEx)(void* output_context, clodb200_group group, const clodb200_cluster* clusters, size_t cluster_count, size_t task_index, unsigned int thread_index);
+
+/* Returns the total number of clusters produced; 0 for empty/invalid geometry (one line on stderr, as clusterlod.h:803-816)
+ * or on failure (clodb200_last_error() is then non-empty). parallel_config of the reference is accepted and ignored. */
+size_t clodb200_build(clodb200_config config, clodb200_mesh mesh, void* output_context, clodb200_output output_callback);
+size_t clodb200_buildEx(clodb200_config config, clodb200_mesh mesh, void* output_context, clodb200_outputEx output_callback, const void* parallel_config);
+
+/* Device-resident variant: upload once, build many times (benchmarks; scene batches). */
+typedef struct clodb200_device_mesh clodb200_device_mesh;
+clodb200_device_mesh* clodb200_meshUpload(clodb200_mesh mesh);
+void clodb200_meshFree(clodb200_device_mesh* mesh);
+size_t clodb200_meshBuildEx(clodb200_config config, const clodb200_device_mesh* mesh, void* output_context, clodb200_outputEx output_callback);
+
+/* Recording build: runs clodb200_meshBuildEx / clodb200_buildEx with an internal callback that stores the whole output
+ * stream, returned as named arrays ("group_depth" i32, "group_simplified" f32x5, "group_cluster_offsets" u32,
+ * "cluster_refined" i32, "cluster_bounds" f32x5, "cluster_vertex_count" u32, "cluster_index_offsets" u64,
+ * "cluster_indices" u32, "level_triangles"/"level_clusters"/"level_groups" u32, "stats" u64). */
+typedef struct clodb200_record clodb200_record;
+clodb200_record* clodb200_buildRecorded(clodb200_config config, clodb200_mesh mesh);
+clodb200_record* clodb200_meshBuildRecorded(clodb200_config config, const clodb200_device_mesh* mesh, int keep_indices);
+int clodb200_recordGet(const clodb200_record* record, const char* name, const void** out_ptr, size_t* out_bytes);
+void clodb200_recordFree(clodb200_record* record);
+
 /* Diagnostics of the last clodb200_simplifyGroups / build on this process: {passes, wavefront rounds, max rounds in a pass}. */
 void clodb200_simplifyStats(unsigned int out3[3]);
 
