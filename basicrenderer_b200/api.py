@@ -281,6 +281,28 @@ class ClodLib:
             raise ClodbError(err)
         return n
 
+    def timer_start(self):
+        self._lib.clodb200_timerStart()
+
+    def timer_stop_ms(self) -> float:
+        self._lib.clodb200_timerStop.restype = C.c_float
+        return float(self._lib.clodb200_timerStop())
+
+    def profile_enable(self, enable: bool):
+        self._lib.clodb200_profileEnable(1 if enable else 0)
+
+    def profile_report(self):
+        """-> list of (kernel, launches, total_ms, total_threads), slowest first"""
+        self._lib.clodb200_profileReport.restype = C.c_size_t
+        self._lib.clodb200_profileReport.argtypes = [C.c_char_p, C.c_size_t]
+        buf = C.create_string_buffer(1 << 20)
+        self._lib.clodb200_profileReport(buf, len(buf))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, count, ms, threads = line.rsplit(",", 3)
+            rows.append((name, int(count), float(ms), int(threads)))
+        return rows
+
     def simplify_stats(self):
         a = (C.c_uint * 3)()
         self._lib.clodb200_simplifyStats(a)

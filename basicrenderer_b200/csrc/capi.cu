@@ -4,6 +4,7 @@
 #include "dag.h"
 
 #include <map>
+#include <algorithm>
 
 #include <mutex>
 
@@ -693,6 +694,65 @@ int clodb200_recordGet(const clodb200_record* record, const char* name, const vo
 void clodb200_recordFree(clodb200_record* record)
 {
 	delete record;
+}
+
+#ifndef CLODB_EMU
+static cudaEvent_t g_timer_start = nullptr, g_timer_stop = nullptr;
+#endif
+
+void clodb200_timerStart(void)
+{
+#ifndef CLODB_EMU
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (!g_timer_start)
+	{
+		cudaEventCreate(&g_timer_start);
+		cudaEventCreate(&g_timer_stop);
+	}
+	cudaStreamSynchronize(g_stream);
+	cudaEventRecord(g_timer_start, g_stream);
+#endif
+}
+
+float clodb200_timerStop(void)
+{
+	float ms = 0.f;
+#ifndef CLODB_EMU
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (!g_timer_start)
+		return 0.f;
+	cudaEventRecord(g_timer_stop, g_stream);
+	cudaEventSynchronize(g_timer_stop);
+	cudaEventElapsedTime(&ms, g_timer_start, g_timer_stop);
+#endif
+	return ms;
+}
+
+void clodb200_profileEnable(int enable)
+{
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	g_profile = enable;
+}
+
+size_t clodb200_profileReport(char* buffer, size_t capacity)
+{
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	std::string report;
+	try
+	{
+		report = profile_report();
+	}
+	catch (const std::exception& e)
+	{
+		report = std::string("error,0,0 ") + e.what() + "\n";
+	}
+	if (buffer && capacity)
+	{
+		size_t n = std::min(capacity - 1, report.size());
+		memcpy(buffer, report.data(), n);
+		buffer[n] = 0;
+	}
+	return report.size() + 1;
 }
 
 void clodb200_simplifyStats(unsigned int out3[3])

@@ -1,12 +1,15 @@
 // clodb200 runtime layer implementation (see rt.cuh).
 #include "rt.cuh"
 
+#include <algorithm>
+
 namespace clodb
 {
 
 stream_t g_stream = 0;
 uint64_t g_launches = 0;
 int g_sync_debug = 0;
+int g_profile = 0;
 
 #ifdef CLODB_EMU
 size_t emu_tid = 0;
@@ -83,6 +86,98 @@ void dev_d2d(void* dst, const void* src, size_t bytes)
 void dev_sync()
 {
 	CUDA_CHECK(cudaStreamSynchronize(g_stream));
+}
+#endif
+
+#ifdef CLODB_EMU
+void profile_mark(const char*, int, size_t)
+{
+}
+std::string profile_report()
+{
+	return std::string();
+}
+#else
+namespace
+{
+struct ProfileSpan
+{
+	const char* name;
+	cudaEvent_t start, stop;
+	size_t threads;
+};
+std::vector<ProfileSpan> g_spans;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t take_event()
+{
+	if (!g_event_pool.empty())
+	{
+		cudaEvent_t e = g_event_pool.back();
+		g_event_pool.pop_back();
+		return e;
+	}
+	cudaEvent_t e;
+	CUDA_CHECK(cudaEventCreate(&e));
+	return e;
+}
+} // namespace
+
+void profile_mark(const char* kernel_name, int end, size_t threads)
+{
+	if (!end)
+	{
+		ProfileSpan s;
+		s.name = kernel_name;
+		s.start = take_event();
+		s.stop = take_event();
+		s.threads = threads;
+		CUDA_CHECK(cudaEventRecord(s.start, g_stream));
+		g_spans.push_back(s);
+	}
+	else if (!g_spans.empty())
+	{
+		CUDA_CHECK(cudaEventRecord(g_spans.back().stop, g_stream));
+	}
+}
+
+std::string profile_report()
+{
+	CUDA_CHECK(cudaStreamSynchronize(g_stream));
+	struct Acc
+	{
+		std::string name;
+		double ms = 0;
+		uint64_t count = 0;
+		uint64_t threads = 0;
+	};
+	std::vector<Acc> accs;
+	for (const ProfileSpan& s : g_spans)
+	{
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, s.start, s.stop));
+		Acc* a = nullptr;
+		for (Acc& x : accs)
+			if (x.name == s.name)
+				a = &x;
+		if (!a)
+		{
+			accs.push_back(Acc());
+			a = &accs.back();
+			a->name = s.name;
+		}
+		a->ms += ms;
+		a->count++;
+		a->threads += s.threads;
+		g_event_pool.push_back(s.start);
+		g_event_pool.push_back(s.stop);
+	}
+	g_spans.clear();
+	std::sort(accs.begin(), accs.end(), [](const Acc& a, const Acc& b) { return a.ms > b.ms; });
+	std::string out;
+	for (const Acc& a : accs)
+		out += a.name + "," + std::to_string(a.count) + "," + std::to_string(a.ms) + "," + std::to_string(a.threads) + "\n";
+	return out;
 }
 #endif
 

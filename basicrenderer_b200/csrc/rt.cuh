@@ -160,7 +160,11 @@ typedef cudaStream_t stream_t;
 		size_t _n = size_t(n);                                                                         \
 		if (_n > 0)                                                                                    \
 		{                                                                                              \
+			if (::clodb::g_profile)                                                                    \
+				::clodb::profile_mark(#kernel, 0, _n);                                                 \
 			kernel<<<(unsigned int)((_n + 255) / 256), 256, 0, ::clodb::g_stream>>>(__VA_ARGS__);       \
+			if (::clodb::g_profile)                                                                    \
+				::clodb::profile_mark(#kernel, 1, 0);                                                     \
 			::clodb::g_launches++;                                                                     \
 			CUDA_CHECK(cudaGetLastError());                                                            \
 			if (::clodb::g_sync_debug)                                                                 \
@@ -174,7 +178,11 @@ typedef cudaStream_t stream_t;
 	{                                                                                                  \
 		if ((grid) > 0)                                                                                \
 		{                                                                                              \
+			if (::clodb::g_profile)                                                                    \
+				::clodb::profile_mark(#kernel, 0, size_t(grid) * size_t(block));                       \
 			kernel<<<(unsigned int)(grid), (block), 0, ::clodb::g_stream>>>(__VA_ARGS__);              \
+			if (::clodb::g_profile)                                                                    \
+				::clodb::profile_mark(#kernel, 1, 0);                                                     \
 			::clodb::g_launches++;                                                                     \
 			CUDA_CHECK(cudaGetLastError());                                                            \
 			if (::clodb::g_sync_debug)                                                                 \
@@ -186,6 +194,12 @@ typedef cudaStream_t stream_t;
 extern stream_t g_stream;
 extern uint64_t g_launches;
 extern int g_sync_debug;
+
+// optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg); off by default
+extern int g_profile;
+void profile_mark(const char* kernel_name, int end, size_t threads);
+// drains recorded events; returns "name,launches,total_ms,total_threads\n" lines sorted by time
+std::string profile_report();
 
 // ---- raw device memory -------------------------------------------------------------------------------------------
 void* dev_malloc(size_t bytes);

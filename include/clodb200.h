@@ -165,6 +165,17 @@ clodb200_record* clodb200_meshBuildRecorded(clodb200_config config, const clodb2
 int clodb200_recordGet(const clodb200_record* record, const char* name, const void** out_ptr, size_t* out_bytes);
 void clodb200_recordFree(clodb200_record* record);
 
+/* CUDA-event stopwatch on the build stream: Start records an event, Stop records another, synchronises and returns the
+ * elapsed device time in milliseconds (bench.py brackets its timed steps with these). */
+void clodb200_timerStart(void);
+float clodb200_timerStop(void);
+
+/* Per-kernel CUDA-event timing on the build stream (off by default; adds two event records per launch).
+ * clodb200_profileReport drains the recorded spans into "kernel,launches,total_ms,total_threads" lines, slowest first; returns the
+ * number of bytes needed (including the terminator); at most `capacity` bytes are written. */
+void clodb200_profileEnable(int enable);
+size_t clodb200_profileReport(char* buffer, size_t capacity);
+
 /* Diagnostics of the last clodb200_simplifyGroups / build on this process: {passes, wavefront rounds, max rounds in a pass}. */
 void clodb200_simplifyStats(unsigned int out3[3]);
 

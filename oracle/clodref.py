@@ -79,6 +79,8 @@ def lib():
         _lib.clodref_clusterize.argtypes = [C.POINTER(ClodConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.clodref_simplify.restype = C.c_size_t
         _lib.clodref_simplify.argtypes = [C.POINTER(ClodConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
+        _lib.clodref_dag_build_mt.restype = C.c_size_t
+        _lib.clodref_dag_build_mt.argtypes = [C.POINTER(ClodConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint]
         _lib.meshopt_computeClusterBounds.restype = None  # struct return handled by wrapper below
     return _lib
 
@@ -164,6 +166,20 @@ def dag_build(positions, indices, attributes=None, attribute_weights=None, prote
     fn = lib().clodref_dag_build_dump if dump else lib().clodref_dag_build
     h = fn(C.byref(cfg), _ptr(indices), indices.size, _ptr(positions), V, pstride, _ptr(attributes), astride, _ptr(attribute_weights), acount, protect_mask, None)
     return Dag(h)
+
+
+def dag_build_timed(positions, indices, attributes=None, attribute_weights=None, protect_mask=0, threads=1, config=None) -> int:
+    """The reference's clodBuildEx with its per-group iteration tasks spread over `threads` host threads; output is
+    discarded (timing runs). Returns the total cluster count."""
+    cfg = config or builder_config()
+    positions = np.ascontiguousarray(positions, dtype=np.float32)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    acount = astride = 0
+    if attributes is not None:
+        attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+        attribute_weights = np.ascontiguousarray(attribute_weights, dtype=np.float32)
+        acount, astride = attribute_weights.size, attributes.shape[1] * 4
+    return lib().clodref_dag_build_mt(C.byref(cfg), _ptr(indices), indices.size, _ptr(positions), positions.shape[0], 12, _ptr(attributes), astride, _ptr(attribute_weights), acount, protect_mask, threads)
 
 
 def position_remap(positions: np.ndarray) -> np.ndarray:

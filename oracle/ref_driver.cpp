@@ -21,6 +21,8 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace
@@ -176,6 +178,65 @@ clodref_handle* clodref_dag_build(const clodConfig* config, const unsigned int* 
 	OutputRecorder recorder(&h->store);
 	h->cluster_count = clodBuildEx(*config, mesh, &recorder, &OutputRecorder::callback, NULL);
 	return h;
+}
+
+// Multi-threaded variant: the reference's own inner-threaded path. clodBuildEx calls the iteration callback once per DAG
+// level; the callback fans the per-group tasks out over `threads` host threads, which is exactly how the renderer drives
+// it through TaskSchedulerManager::ParallelFor (ClusterLODUtilities.cpp:5587-5593). No output is recorded unless
+// `record` is non-zero (timing runs).
+struct MtContext
+{
+	unsigned int threads;
+};
+
+static void mtIterate(void* iteration_context, void* output_context, int, size_t task_count)
+{
+	// output_context is the recorder/discard context; the thread count travels in a static
+	(void)output_context;
+	extern unsigned int g_clodref_threads;
+	unsigned int n = g_clodref_threads ? g_clodref_threads : 1;
+	if (n <= 1 || task_count <= 1)
+	{
+		for (size_t i = 0; i < task_count; ++i)
+			clodBuild_iterationTask(iteration_context, i, 0);
+		return;
+	}
+	std::atomic<size_t> next(0);
+	std::vector<std::thread> pool;
+	auto worker = [&](unsigned int tid) {
+		for (;;)
+		{
+			size_t i = next.fetch_add(1);
+			if (i >= task_count)
+				break;
+			clodBuild_iterationTask(iteration_context, i, tid);
+		}
+	};
+	unsigned int count = unsigned(std::min<size_t>(n, task_count));
+	for (unsigned int t = 1; t < count; ++t)
+		pool.emplace_back(worker, t);
+	worker(0);
+	for (std::thread& t : pool)
+		t.join();
+}
+
+unsigned int g_clodref_threads = 1;
+
+static int discardCallback(void* ctx, clodGroup, const clodCluster*, size_t, size_t, unsigned int)
+{
+	int* next = static_cast<int*>(ctx);
+	return (*next)++;
+}
+
+size_t clodref_dag_build_mt(const clodConfig* config, const unsigned int* indices, size_t index_count, const float* positions, size_t vertex_count, size_t positions_stride,
+    const float* attributes, size_t attributes_stride, const float* attribute_weights, size_t attribute_count, unsigned int protect_mask, unsigned int threads)
+{
+	clodMesh mesh = makeMesh(indices, index_count, positions, vertex_count, positions_stride, attributes, attributes_stride, attribute_weights, attribute_count, protect_mask, NULL);
+	g_clodref_threads = threads;
+	clodBuildParallelConfig parallel = {};
+	parallel.iteration_callback = &mtIterate;
+	int next = 0;
+	return clodBuildEx(*config, mesh, &next, &discardCallback, &parallel);
 }
 
 // Same loop as clodBuildEx (clusterlod.h:792-943) expressed with the reference's own clod:: functions, recording
