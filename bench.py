@@ -103,10 +103,8 @@ def _pin(a: np.ndarray) -> np.ndarray:
     import torch
 
     t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    arr = t.numpy()
-    arr._pinned_owner = t if hasattr(arr, "__dict__") else None
-    _PINNED.append(t)
-    return arr
+    _PINNED.append(t)  # keep the pinned allocation alive for the numpy view
+    return t.numpy()
 
 
 _PINNED = []
@@ -185,6 +183,11 @@ def run_ours(args):
         rows = lib.profile_report()
         lib.profile_enable(False)
         total_kernel_ms = sum(r[2] for r in rows)
+        if os.environ.get("CLODB200_PROFILE_OUT"):
+            with open(os.environ["CLODB200_PROFILE_OUT"], "w") as f:
+                f.write("kernel,launches,total_ms,total_threads\n")
+                for r in rows:
+                    f.write(f"{r[0]},{r[1]},{r[2]:.4f},{r[3]}\n")
         top = rows[0]
         peaks = {}
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
