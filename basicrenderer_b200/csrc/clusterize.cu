@@ -453,57 +453,25 @@ DEVFN ScanElem block_scan_exclusive(const ScanElem& agg, ScanElem* smem /* 8 */,
 	return scan_combine(warp_prefix, ex);
 }
 
-static __global__ void k_sa_reduce(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, ScanElem* tile_agg, u32 T, int backward)
+struct OpSegBox
 {
-	__shared__ ScanElem smem[SA_THREADS / 32];
-	u32 base = blockIdx.x * SA_TILE + threadIdx.x * SA_ITEMS;
-	ScanElem agg = scan_identity();
-#pragma unroll
-	for (int k = 0; k < SA_ITEMS; ++k)
-		agg = scan_combine(agg, load_elem(boxes, order, node_of_pos, node_begin, node_count, T, base + k, backward != 0));
-	ScanElem total;
-	block_scan_exclusive(agg, smem, &total);
-	if (threadIdx.x == 0)
-		tile_agg[blockIdx.x] = total;
-}
-
-// exclusive scan of tile aggregates by one warp (sequential over chunks of 32)
-static __global__ void k_sa_tiles(ScanElem* tile_agg, u32 tiles)
-{
-	int lane = threadIdx.x;
-	ScanElem carry = scan_identity();
-	for (u32 base = 0; base < tiles; base += 32)
+	DEVFN ScanElem identity()
 	{
-		u32 i = base + lane;
-		ScanElem v = i < tiles ? tile_agg[i] : scan_identity();
-		ScanElem inc = v;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			ScanElem t = scan_shfl_up(inc, d);
-			if (lane >= d)
-				inc = scan_combine(t, inc);
-		}
-		ScanElem ex = scan_shfl_up(inc, 1);
-		if (lane == 0)
-			ex = scan_identity();
-		ex = scan_combine(carry, ex);
-		if (i < tiles)
-			tile_agg[i] = ex;
-		ScanElem last = scan_combine(carry, inc);
-		// broadcast lane 31's inclusive value as the next carry
-		for (int k = 0; k < 3; ++k)
-		{
-			carry.mn[k] = __shfl_sync(0xffffffffu, last.mn[k], 31);
-			carry.mx[k] = __shfl_sync(0xffffffffu, last.mx[k], 31);
-		}
-		carry.flag = __shfl_sync(0xffffffffu, last.flag, 31);
+		return scan_identity();
 	}
-}
+	DEVFN ScanElem apply(const ScanElem& a, const ScanElem& b)
+	{
+		return scan_combine(a, b);
+	}
+};
 
-static __global__ void k_sa_apply(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const ScanElem* __restrict__ tile_agg, float* out_area, u32 T, int backward)
+// Segmented inclusive min/max scan of the triangle boxes along one axis order -> surface area at every position, in one
+// chained pass (prims.cuh): per element it reads order u32 + node id u32 + the gathered 32-byte box and writes one f32.
+static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count,
+    float* out_area, u32 T, int backward, u32* chain_flags, char* chain_aggregate, char* chain_inclusive, u32 epoch)
 {
 	__shared__ ScanElem smem[SA_THREADS / 32];
+	__shared__ ScanElem s_prefix;
 	u32 base = blockIdx.x * SA_TILE + threadIdx.x * SA_ITEMS;
 	ScanElem e[SA_ITEMS];
 	ScanElem agg = scan_identity();
@@ -513,7 +481,16 @@ static __global__ void k_sa_apply(const Box* __restrict__ boxes, const u32* __re
 		e[k] = load_elem(boxes, order, node_of_pos, node_begin, node_count, T, base + k, backward != 0);
 		agg = scan_combine(agg, e[k]);
 	}
-	ScanElem prefix = scan_combine(tile_agg[blockIdx.x], block_scan_exclusive(agg, smem, nullptr));
+	ScanElem total;
+	ScanElem ex = block_scan_exclusive(agg, smem, &total);
+	if (threadIdx.x < 32)
+	{
+		ScanElem prefix = scan_chain_lookback<ScanElem, OpSegBox>(blockIdx.x, total, chain_flags, chain_aggregate, chain_inclusive, epoch);
+		if (threadIdx.x == 0)
+			s_prefix = prefix;
+	}
+	__syncthreads();
+	ScanElem prefix = scan_combine(s_prefix, ex);
 #pragma unroll
 	for (int k = 0; k < SA_ITEMS; ++k)
 	{
@@ -528,14 +505,12 @@ static __global__ void k_sa_apply(const Box* __restrict__ boxes, const u32* __re
 	}
 }
 
-static void seg_area_scan(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* out_area, u32 T, bool backward, Arena& temp)
+static void seg_area_scan(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* out_area, u32 T, bool backward, Arena&)
 {
-	ArenaScope scope(temp);
 	u32 tiles = (T + SA_TILE - 1) / SA_TILE;
-	ScanElem* tile_agg = temp.alloc<ScanElem>(tiles);
-	LAUNCH_GRID(k_sa_reduce, tiles, SA_THREADS, boxes, order, node_of_pos, node_begin, node_count, tile_agg, T, backward ? 1 : 0);
-	LAUNCH_GRID(k_sa_tiles, 1, 32, tile_agg, tiles);
-	LAUNCH_GRID(k_sa_apply, tiles, SA_THREADS, boxes, order, node_of_pos, node_begin, node_count, tile_agg, out_area, T, backward ? 1 : 0);
+	scan_chain_reserve(tiles);
+	u32 epoch = scan_chain_next_epoch();
+	LAUNCH_GRID(k_sa_chained, tiles, SA_THREADS, boxes, order, node_of_pos, node_begin, node_count, out_area, T, backward ? 1 : 0, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch);
 }
 #endif
 

@@ -164,64 +164,187 @@ DEVFN T block_exclusive_scan(T v, T* block_total, T* smem)
 	return result;
 }
 
-template <typename T, typename Op>
-__global__ void k_scan_reduce(const T* __restrict__ in, T* __restrict__ block_sums, size_t n)
+// ---- single-pass chained scan ("decoupled look-back") ---------------------------------------------------------------
+// Every tile publishes its aggregate, then its inclusive prefix, in a per-tile descriptor; a tile's exclusive prefix is
+// assembled by warp 0 walking predecessor descriptors 32 at a time. One launch, each input element read once and written
+// once. Descriptor flags carry the epoch of the scan call, so the descriptor arrays are never cleared between calls.
+// Tiles are taken in blockIdx order (CTAs are dispatched in ascending blockIdx, so a predecessor is always resident or
+// finished). The combine is applied in predecessor order, so non-commutative (segmented) operators are supported.
+struct ScanChain
 {
-	__shared__ T smem[34];
-	size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
-	T sum = Op::identity();
+	u32* flags = nullptr;    // per tile: (epoch << 2) | {1 = aggregate ready, 2 = inclusive prefix ready}
+	char* aggregate = nullptr; // SCAN_CHAIN_VALUE_BYTES per tile
+	char* inclusive = nullptr;
+	size_t capacity_tiles = 0;
+	u32 epoch = 0;
+};
+static const int SCAN_CHAIN_VALUE_BYTES = 32;
+extern ScanChain g_scan_chain;
+void scan_chain_reserve(size_t tiles);
+
+// returns the next epoch (never 0 in the low 30 bits, so stale or zeroed descriptors never match)
+static inline u32 scan_chain_next_epoch()
+{
+	g_scan_chain.epoch = (g_scan_chain.epoch + 1) & 0x3fffffffu;
+	if (g_scan_chain.epoch == 0)
+		g_scan_chain.epoch = 1;
+	return g_scan_chain.epoch;
+}
+
+DEVFN u32 ld_volatile_u32(const u32* p)
+{
+	return *reinterpret_cast<const volatile u32*>(p);
+}
+
+template <typename T>
+DEVFN T ld_cg_value(const char* base, size_t tile)
+{
+	// descriptor payloads are written by other CTAs: read through L2
+	const T* p = reinterpret_cast<const T*>(base + tile * SCAN_CHAIN_VALUE_BYTES);
+	T v;
+	u32* dst = reinterpret_cast<u32*>(&v);
+	const u32* src = reinterpret_cast<const u32*>(p);
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k)
-		if (base + k < n)
-			sum = Op::apply(sum, in[base + k]);
-	T total;
-	block_exclusive_scan<T, Op>(sum, &total, smem);
-	if (threadIdx.x == 0)
-		block_sums[blockIdx.x] = total;
+	for (int k = 0; k < int(sizeof(T) / 4); ++k)
+		dst[k] = __ldcg(src + k);
+	return v;
 }
 
-// single-CTA scan of the per-tile sums (1024 threads, looping with a running carry)
-template <typename T, typename Op>
-__global__ void k_scan_blocksums(T* __restrict__ block_sums, size_t nblocks, T* __restrict__ total_out)
+template <typename T>
+DEVFN void st_value(char* base, size_t tile, const T& v)
 {
-	__shared__ T smem[34];
-	__shared__ T carry_s;
-	if (threadIdx.x == 0)
-		carry_s = Op::identity();
-	__syncthreads();
-	for (size_t base = 0; base < nblocks; base += blockDim.x)
+	*reinterpret_cast<T*>(base + tile * SCAN_CHAIN_VALUE_BYTES) = v;
+}
+
+template <typename T>
+DEVFN T shfl_down_struct(const T& v, int d)
+{
+	T r;
+	const u32* src = reinterpret_cast<const u32*>(&v);
+	u32* dst = reinterpret_cast<u32*>(&r);
+#pragma unroll
+	for (int k = 0; k < int(sizeof(T) / 4); ++k)
+		dst[k] = __shfl_down_sync(0xffffffffu, src[k], d);
+	return r;
+}
+
+template <typename T>
+DEVFN T shfl_idx_struct(const T& v, int lane)
+{
+	T r;
+	const u32* src = reinterpret_cast<const u32*>(&v);
+	u32* dst = reinterpret_cast<u32*>(&r);
+#pragma unroll
+	for (int k = 0; k < int(sizeof(T) / 4); ++k)
+		dst[k] = __shfl_sync(0xffffffffu, src[k], lane);
+	return r;
+}
+
+// Called by all 32 lanes of warp 0 with the tile's aggregate; returns the tile's exclusive prefix (valid in every lane)
+// and publishes the tile's inclusive prefix. Combine(a, b): a precedes b.
+template <typename T, typename Op>
+DEVFN T scan_chain_lookback(u32 tile, const T& tile_aggregate, u32* flags, char* aggregate, char* inclusive, u32 epoch)
+{
+	int lane = threadIdx.x & 31;
+	u32 tag_agg = (epoch << 2) | 1u, tag_inc = (epoch << 2) | 2u;
+	if (tile == 0)
 	{
-		size_t i = base + threadIdx.x;
-		T v = i < nblocks ? block_sums[i] : Op::identity();
-		T total;
-		T ex = block_exclusive_scan<T, Op>(v, &total, smem);
-		T carry = carry_s;
-		if (i < nblocks)
-			block_sums[i] = Op::apply(carry, ex);
-		__syncthreads();
-		if (threadIdx.x == 0)
-			carry_s = Op::apply(carry, total);
-		__syncthreads();
+		if (lane == 0)
+		{
+			st_value<T>(inclusive, 0, tile_aggregate);
+			__threadfence();
+			*reinterpret_cast<volatile u32*>(flags) = tag_inc;
+		}
+		return Op::identity();
 	}
-	if (threadIdx.x == 0 && total_out)
-		*total_out = carry_s;
+	if (lane == 0)
+	{
+		st_value<T>(aggregate, tile, tile_aggregate);
+		__threadfence();
+		*reinterpret_cast<volatile u32*>(flags + tile) = tag_agg;
+	}
+	T prefix = Op::identity(); // combination of the predecessors visited so far (nearest block of them)
+	int p = int(tile) - 1;
+	for (;;)
+	{
+		int idx = p - lane;
+		u32 f;
+		for (;;)
+		{
+			f = idx >= 0 ? ld_volatile_u32(flags + idx) : tag_inc;
+			bool ready = f == tag_agg || f == tag_inc;
+			if (__all_sync(0xffffffffu, ready))
+				break;
+		}
+		__threadfence();
+		unsigned inc_mask = __ballot_sync(0xffffffffu, f == tag_inc);
+		int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32; // nearest predecessor whose inclusive prefix is known
+		T v = Op::identity();
+		if (idx >= 0 && lane <= first_inc)
+			v = f == tag_inc ? ld_cg_value<T>(inclusive, size_t(idx)) : ld_cg_value<T>(aggregate, size_t(idx));
+		// ordered reduction: lane L is farther back than lane L-1, so it is the left operand
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			T t = shfl_down_struct(v, d);
+			if (lane + d < 32)
+				v = Op::apply(t, v);
+		}
+		v = shfl_idx_struct(v, 0);
+		prefix = Op::apply(v, prefix);
+		if (inc_mask)
+			break;
+		p -= 32;
+	}
+	if (lane == 0)
+	{
+		st_value<T>(inclusive, tile, Op::apply(prefix, tile_aggregate));
+		__threadfence();
+		*reinterpret_cast<volatile u32*>(flags + tile) = tag_inc;
+	}
+	return prefix;
 }
 
 template <typename T, typename Op>
-__global__ void k_scan_apply(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ block_sums, size_t n)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const T* __restrict__ in, T* __restrict__ out, size_t n, u32* flags, char* aggregate, char* inclusive, u32 epoch, T* __restrict__ total_out)
 {
 	__shared__ T smem[34];
+	__shared__ T s_prefix;
 	size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
 	T v[SCAN_ITEMS];
+	if (base + SCAN_ITEMS <= n)
+	{
+		// SCAN_ITEMS contiguous elements per thread: 16-byte vector loads
+		const uint4* src = reinterpret_cast<const uint4*>(in + base);
+		uint4* dst = reinterpret_cast<uint4*>(v);
+#pragma unroll
+		for (int k = 0; k < int(sizeof(T) * SCAN_ITEMS / 16); ++k)
+			dst[k] = src[k];
+	}
+	else
+	{
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; ++k)
+			v[k] = base + k < n ? in[base + k] : Op::identity();
+	}
 	T sum = Op::identity();
 #pragma unroll
 	for (int k = 0; k < SCAN_ITEMS; ++k)
-	{
-		v[k] = base + k < n ? in[base + k] : Op::identity();
 		sum = Op::apply(sum, v[k]);
-	}
 	T total;
-	T run = Op::apply(block_sums[blockIdx.x], block_exclusive_scan<T, Op>(sum, &total, smem));
+	T ex = block_exclusive_scan<T, Op>(sum, &total, smem);
+	if (threadIdx.x < 32)
+	{
+		T prefix = scan_chain_lookback<T, Op>(blockIdx.x, total, flags, aggregate, inclusive, epoch);
+		if (threadIdx.x == 0)
+		{
+			s_prefix = prefix;
+			if (total_out && blockIdx.x == gridDim.x - 1)
+				*total_out = Op::apply(prefix, total);
+		}
+	}
+	__syncthreads();
+	T run = Op::apply(s_prefix, ex);
 #pragma unroll
 	for (int k = 0; k < SCAN_ITEMS; ++k)
 	{
@@ -229,15 +352,27 @@ __global__ void k_scan_apply(const T* __restrict__ in, T* __restrict__ out, cons
 		v[k] = run;
 		run = Op::apply(run, t);
 	}
+	if (base + SCAN_ITEMS <= n)
+	{
+		uint4* dst = reinterpret_cast<uint4*>(out + base);
+		const uint4* src = reinterpret_cast<const uint4*>(v);
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k)
-		if (base + k < n)
-			out[base + k] = v[k];
+		for (int k = 0; k < int(sizeof(T) * SCAN_ITEMS / 16); ++k)
+			dst[k] = src[k];
+	}
+	else
+	{
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; ++k)
+			if (base + k < n)
+				out[base + k] = v[k];
+	}
 }
 
-// out[i] = op(in[0..i)), in-place allowed; optional device-side total
+// out[i] = op(in[0..i)), in-place allowed; optional device-side total. `in`/`out` must be 16-byte aligned (arena
+// allocations are 256-byte aligned).
 template <typename T, typename Op>
-static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena& arena)
+static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena&)
 {
 	if (n == 0)
 	{
@@ -245,12 +380,10 @@ static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena
 			dev_memset(total, 0, sizeof(T));
 		return;
 	}
-	ArenaScope scope(arena);
 	size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-	T* block_sums = arena.alloc<T>(nblocks);
-	LAUNCH_GRID((k_scan_reduce<T, Op>), nblocks, SCAN_THREADS, in, block_sums, n);
-	LAUNCH_GRID((k_scan_blocksums<T, Op>), 1, 1024, block_sums, nblocks, total);
-	LAUNCH_GRID((k_scan_apply<T, Op>), nblocks, SCAN_THREADS, in, out, block_sums, n);
+	scan_chain_reserve(nblocks);
+	u32 epoch = scan_chain_next_epoch();
+	LAUNCH_GRID((k_scan_chained<T, Op>), nblocks, SCAN_THREADS, in, out, n, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch, total);
 }
 
 // ---- radix sort ------------------------------------------------------------------------------------------------

@@ -1,5 +1,5 @@
 // clodb200 runtime layer implementation (see rt.cuh).
-#include "rt.cuh"
+#include "prims.cuh"
 
 #include <algorithm>
 
@@ -178,6 +178,26 @@ std::string profile_report()
 	for (const Acc& a : accs)
 		out += a.name + "," + std::to_string(a.count) + "," + std::to_string(a.ms) + "," + std::to_string(a.threads) + "\n";
 	return out;
+}
+#endif
+
+#ifndef CLODB_EMU
+ScanChain g_scan_chain;
+
+void scan_chain_reserve(size_t tiles)
+{
+	if (tiles <= g_scan_chain.capacity_tiles)
+		return;
+	size_t cap = std::max<size_t>(tiles * 2, size_t(1) << 16);
+	CUDA_CHECK(cudaStreamSynchronize(g_stream));
+	dev_free(g_scan_chain.flags);
+	dev_free(g_scan_chain.aggregate);
+	dev_free(g_scan_chain.inclusive);
+	g_scan_chain.flags = static_cast<u32*>(dev_malloc(cap * sizeof(u32)));
+	g_scan_chain.aggregate = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
+	g_scan_chain.inclusive = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
+	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.flags, 0, cap * sizeof(u32), g_stream));
+	g_scan_chain.capacity_tiles = cap;
 }
 #endif
 

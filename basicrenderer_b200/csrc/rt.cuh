@@ -189,6 +189,24 @@ typedef cudaStream_t stream_t;
 				CUDA_CHECK(cudaStreamSynchronize(::clodb::g_stream));                                  \
 		}                                                                                              \
 	} while (0)
+
+// cooperative launch (grid-wide barriers inside the kernel); the caller sizes the grid to be co-resident
+#define LAUNCH_COOP(kernel, grid, block, args_struct)                                                  \
+	do                                                                                                 \
+	{                                                                                                  \
+		if ((grid) > 0)                                                                                \
+		{                                                                                              \
+			if (::clodb::g_profile)                                                                    \
+				::clodb::profile_mark(#kernel, 0, size_t(grid) * size_t(block));                       \
+			void* _args[] = {(void*)&(args_struct)};                                                   \
+			CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned int)(grid)), dim3(block), _args, 0, ::clodb::g_stream)); \
+			if (::clodb::g_profile)                                                                    \
+				::clodb::profile_mark(#kernel, 1, 0);                                                  \
+			::clodb::g_launches++;                                                                     \
+			if (::clodb::g_sync_debug)                                                                 \
+				CUDA_CHECK(cudaStreamSynchronize(::clodb::g_stream));                                  \
+		}                                                                                              \
+	} while (0)
 #endif
 
 extern stream_t g_stream;

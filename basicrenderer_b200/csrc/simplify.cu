@@ -20,6 +20,9 @@
 //     sequence and are applied as a per-group cut afterwards.
 #include "clodb.h"
 
+#ifndef CLODB_EMU
+#include <cooperative_groups.h>
+#endif
 #include <cfloat>
 #include <cmath>
 #include <algorithm>
@@ -639,6 +642,32 @@ KERNEL k_group_minmax(const u32* __restrict__ sv_global, const u32* __restrict__
 		return;
 	const float* p = positions + size_t(sv_global[s]) * 3;
 	u32 g = sv_group[s];
+#ifndef CLODB_EMU
+	// sparse vertices are numbered group by group, so a warp almost always sits in one group: reduce in registers and
+	// issue one atomic per warp and component instead of 32 contending ones
+	unsigned active = __activemask();
+	u32 g0 = __shfl_sync(active, g, __ffs(active) - 1);
+	if (active == 0xffffffffu && __all_sync(active, g == g0))
+	{
+		for (int k = 0; k < 3; ++k)
+		{
+			u32 key = float_order_key(p[k]);
+			u32 lo = key, hi = key;
+			for (int d = 16; d >= 1; d >>= 1)
+			{
+				u32 olo = __shfl_xor_sync(0xffffffffu, lo, d), ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+				lo = olo < lo ? olo : lo;
+				hi = ohi > hi ? ohi : hi;
+			}
+			if ((threadIdx.x & 31) == 0)
+			{
+				atomicMin(&gmin[g * 3 + k], lo);
+				atomicMax(&gmax[g * 3 + k], hi);
+			}
+		}
+		return;
+	}
+#endif
 	for (int k = 0; k < 3; ++k)
 	{
 		// the reference keeps the first value unless strictly smaller/larger; with -0/+0 ties the order key orders -0 < +0,
@@ -950,21 +979,14 @@ KERNEL k_collapse_init(u32* collapse_remap, u8* collapse_locked, u32 vertex_coun
 }
 
 // publish, per canonical vertex, the lowest sorted position among still-undecided candidates touching it
-KERNEL k_wave_publish(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap,
-    u64* vmin_any, u64* vmin_src, u32 round_tag, u32 cand_total, u32* undecided_count)
+DEVFN void wave_publish_item(u32 k, const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, u64* vmin_any, u64* vmin_src, u32 round_tag)
 {
-	size_t k = GTID;
-	if (k >= cand_total)
-		return;
-	if (status[k] != Status_Undecided)
-		return;
 	u32 c = sorted_cand[k];
 	u32 r0 = remap[cand_v0[c]], r1 = remap[cand_v1[c]];
 	u64 value = (u64(~round_tag) << 32) | u64(k);
 	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_any[r0]), (unsigned long long)value);
 	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_any[r1]), (unsigned long long)value);
 	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_src[r0]), (unsigned long long)value);
-	atomicAdd(undecided_count, 1u);
 }
 
 DEVFN u32 wave_min(const u64* vmin, u32 v, u32 round_tag)
@@ -973,16 +995,11 @@ DEVFN u32 wave_min(const u64* vmin, u32 v, u32 round_tag)
 	return u32(x >> 32) == ~round_tag ? u32(x) : NONE;
 }
 
-KERNEL k_wave_decide(const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, const u32* __restrict__ wedge, const u8* __restrict__ kind,
+// One dependency-wavefront step for the undecided candidate at sorted position k; returns true while it stays undecided.
+DEVFN bool wave_decide_item(u32 k, const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, const u32* __restrict__ wedge, const u8* __restrict__ kind,
     const u32* __restrict__ loop, const u32* __restrict__ loopback, const Vector3* __restrict__ vpos, const u32* __restrict__ idx, const u32* __restrict__ adj_off, const u32* __restrict__ adj_corner,
-    const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked, u32 cand_total)
+    const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked)
 {
-	size_t kk = GTID;
-	if (kk >= cand_total)
-		return;
-	u32 k = u32(kk);
-	if (status[k] != Status_Undecided)
-		return;
 	u32 c = sorted_cand[k];
 	u32 i0 = cand_v0[c], i1 = cand_v1[c];
 	u32 r0 = remap[i0], r1 = remap[i1];
@@ -991,17 +1008,17 @@ KERNEL k_wave_decide(const u32* __restrict__ sorted_cand, u8* status, const u32*
 	if (collapse_locked[r0] | collapse_locked[r1])
 	{
 		status[k] = Status_Locked;
-		return;
+		return false;
 	}
 	if (wave_min(vmin_any, r0, round_tag) != k || wave_min(vmin_any, r1, round_tag) != k)
-		return;
+		return true;
 	// the flip test reads collapse_remap of r0's neighbours: wait for lower-ranked collapses that could move them
 	for (u32 e = adj_off[r0]; e < adj_off[r0 + 1]; ++e)
 	{
 		u32 corner = adj_corner[e];
 		u32 a = remap[idx[corner_next(corner)]], b = remap[idx[corner_prev(corner)]];
 		if (wave_min(vmin_src, a, round_tag) < k || wave_min(vmin_src, b, round_tag) < k)
-			return;
+			return true;
 	}
 
 	// hasTriangleFlips(adjacency, vertex_positions, collapse_remap, r0, r1)
@@ -1018,7 +1035,7 @@ KERNEL k_wave_decide(const u32* __restrict__ sorted_cand, u8* status, const u32*
 			if (has_triangle_flip(vpos[a], vpos[b], v0, v1))
 			{
 				status[k] = Status_Flip;
-				return;
+				return false;
 			}
 		}
 	}
@@ -1048,7 +1065,114 @@ KERNEL k_wave_decide(const u32* __restrict__ sorted_cand, u8* status, const u32*
 	collapse_locked[r0] = 1;
 	collapse_locked[r1] = 1;
 	status[k] = Status_Performed;
+	return false;
 }
+
+#ifdef CLODB_EMU
+// development emulation: one publish + one decide sweep over all candidates per round
+KERNEL k_wave_publish(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap,
+    u64* vmin_any, u64* vmin_src, u32 round_tag, u32 cand_total, u32* undecided_count)
+{
+	size_t k = GTID;
+	if (k >= cand_total || status[k] != Status_Undecided)
+		return;
+	wave_publish_item(u32(k), sorted_cand, cand_v0, cand_v1, remap, vmin_any, vmin_src, round_tag);
+	atomicAdd(undecided_count, 1u);
+}
+
+KERNEL k_wave_decide(const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, const u32* __restrict__ wedge, const u8* __restrict__ kind,
+    const u32* __restrict__ loop, const u32* __restrict__ loopback, const Vector3* __restrict__ vpos, const u32* __restrict__ idx, const u32* __restrict__ adj_off, const u32* __restrict__ adj_corner,
+    const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked, u32 cand_total)
+{
+	size_t k = GTID;
+	if (k >= cand_total || status[k] != Status_Undecided)
+		return;
+	wave_decide_item(u32(k), sorted_cand, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked);
+}
+#else
+// Persistent cooperative kernel: all wavefront rounds of a pass in one launch. The undecided candidates are kept as a
+// compacted work list (double buffered, warp-aggregated appends), so a round only touches what is still undecided;
+// rounds are separated by grid-wide barriers instead of kernel launches.
+//   state[0..1] list counters (zero on entry), state[2] running round tag, state[3] rounds executed, state[4] undecided left,
+//   state[5] total rounds of all passes, state[6] max rounds in a pass
+struct WaveArgs
+{
+	const u32* sorted_cand;
+	u8* status;
+	const u32 *cand_v0, *cand_v1, *remap, *wedge;
+	const u8* kind;
+	const u32 *loop, *loopback;
+	const Vector3* vpos;
+	const u32 *idx, *adj_off, *adj_corner;
+	u64 *vmin_any, *vmin_src;
+	u32* collapse_remap;
+	u8* collapse_locked;
+	u32* list[2];
+	u32* state;
+	u32 cand_total, max_rounds;
+};
+
+static __global__ void __launch_bounds__(256) k_wave_rounds(WaveArgs a)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const u32 gsize = gridDim.x * blockDim.x;
+	const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 lane = threadIdx.x & 31;
+	u32 n = a.cand_total;
+	u32 tag = a.state[2];
+	const u32* cur = nullptr; // null: identity list 0..n-1
+	u32 round = 0;
+	for (;;)
+	{
+		++round;
+		++tag;
+		for (u32 i = gtid; i < n; i += gsize)
+			wave_publish_item(cur ? cur[i] : i, a.sorted_cand, a.cand_v0, a.cand_v1, a.remap, a.vmin_any, a.vmin_src, tag);
+		grid.sync();
+		u32* next = a.list[round & 1];
+		u32* counter = a.state + (round & 1);
+		if (gtid == 0)
+			a.state[(round + 1) & 1] = 0;
+		for (u32 base = gtid - lane; base < n; base += gsize)
+		{
+			u32 i = base + lane;
+			u32 k = 0;
+			bool undecided = false;
+			if (i < n)
+			{
+				k = cur ? cur[i] : i;
+				undecided = wave_decide_item(k, a.sorted_cand, a.status, a.cand_v0, a.cand_v1, a.remap, a.wedge, a.kind, a.loop, a.loopback, a.vpos, a.idx, a.adj_off, a.adj_corner, a.vmin_any, a.vmin_src, tag, a.collapse_remap,
+				    a.collapse_locked);
+			}
+			unsigned mask = __ballot_sync(0xffffffffu, undecided);
+			if (mask)
+			{
+				u32 off = 0;
+				if (lane == 0)
+					off = atomicAdd(counter, u32(__popc(mask)));
+				off = __shfl_sync(0xffffffffu, off, 0);
+				if (undecided)
+					next[off + __popc(mask & ((1u << lane) - 1))] = k;
+			}
+		}
+		grid.sync();
+		n = *reinterpret_cast<volatile u32*>(counter);
+		if (n == 0 || round >= a.max_rounds)
+			break;
+		cur = next;
+	}
+	if (gtid == 0)
+	{
+		a.state[2] = tag;
+		a.state[3] = round;
+		a.state[4] = n;
+		a.state[5] += round;
+		a.state[6] = a.state[6] > round ? a.state[6] : round;
+	}
+}
+#endif
+
+
 
 // per sorted position: triangle weight / flip flag / tagged error for the prefix scans behind the serial early-outs
 KERNEL k_cut_inputs(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_group, const float* __restrict__ cand_error, const u8* __restrict__ kind,
@@ -1098,10 +1222,11 @@ KERNEL k_cut_find(const u32* __restrict__ sorted_cand, const u8* __restrict__ st
 		if (error > error_goal && error > result_error && tris_before > goal / 6)
 			stop = true;
 	}
-	if (stop)
-		atomicMin(&gs.cut, k);
 	// undecided candidates (round cap reached) also end the pass for their group: nothing after them is trustworthy
 	if (status[k] == Status_Undecided)
+		stop = true;
+	// every position past the first stop also stops: test the current minimum first so only a few atomics are issued
+	if (stop && k < *reinterpret_cast<volatile u32*>(&gs.cut))
 		atomicMin(&gs.cut, k);
 }
 
@@ -1498,6 +1623,19 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 
 	dev_memset(vmin_any, 0xff, size_t(vertex_count) * 8);
 	dev_memset(vmin_src, 0xff, size_t(vertex_count) * 8);
+#ifndef CLODB_EMU
+	u32* wave_state = temp.alloc<u32>(8);
+	dev_memset(wave_state, 0, 8 * sizeof(u32));
+	static u32 wave_max_blocks = 0;
+	if (!wave_max_blocks)
+	{
+		int per_sm = 0, device = 0, sms = 0;
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wave_rounds, 256, 0));
+		CUDA_CHECK(cudaGetDevice(&device));
+		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+		wave_max_blocks = u32(std::max(1, per_sm) * sms);
+	}
+#endif
 
 	u32 cur_T = T;
 	u32 round_tag = 0;
@@ -1528,6 +1666,7 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		dev_memset(status, 0, cand_total);
 
 		u32 rounds = 0;
+#ifdef CLODB_EMU
 		for (;;)
 		{
 			round_tag++;
@@ -1542,6 +1681,20 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 					break;
 			}
 		}
+#else
+		{
+			WaveArgs wa;
+			wa.sorted_cand = sort_val, wa.status = status, wa.cand_v0 = cand_v0, wa.cand_v1 = cand_v1, wa.remap = remap, wa.wedge = wedge, wa.kind = kind, wa.loop = loop, wa.loopback = loopback;
+			wa.vpos = vpos, wa.idx = idx, wa.adj_off = adj_off, wa.adj_corner = adj_corner, wa.vmin_any = vmin_any, wa.vmin_src = vmin_src, wa.collapse_remap = collapse_remap, wa.collapse_locked = collapse_locked;
+			wa.list[0] = tri_weight; // the cut-scan inputs are not live during the rounds: reuse them as the two work lists
+			wa.list[1] = flip_flag;
+			wa.state = wave_state;
+			wa.cand_total = cand_total, wa.max_rounds = config_max_rounds();
+			dev_memset(wave_state, 0, 2 * sizeof(u32));
+			u32 blocks = std::min<u32>(wave_max_blocks, (cand_total + 255) / 256);
+			LAUNCH_COOP(k_wave_rounds, blocks, 256, wa);
+		}
+#endif
 		g_simplify_stats.rounds += rounds;
 		g_simplify_stats.max_rounds = std::max(g_simplify_stats.max_rounds, rounds);
 
@@ -1573,6 +1726,13 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		any_active = dev_read(scalars + 1) != 0;
 	}
 
+#ifndef CLODB_EMU
+	{
+		std::vector<u32> st = dev_download(wave_state, 8);
+		g_simplify_stats.rounds = st[5];
+		g_simplify_stats.max_rounds = st[6];
+	}
+#endif
 	LAUNCH(k_finalize_output, size_t(cur_T) * 3, idx, sv_global, out.tri, size_t(cur_T) * 3);
 	LAUNCH(k_group_results, G, groups, group_extent, out.group_tri_offset, out.group_error, G);
 	out.triangle_count = cur_T;
