@@ -837,6 +837,8 @@ struct GroupState
 	u32 cand_count;
 	u32 cut;           // global sorted position where the serial scan would have stopped
 	float result_error;
+	u32 win_begin;     // sorted positions [win_begin, win_end) are the candidates examined by the current wavefront run
+	u32 win_end;
 };
 
 // one slot per triangle edge; flag + direction info (pickEdgeCollapses)
@@ -1069,31 +1071,32 @@ DEVFN bool wave_decide_item(u32 k, const u32* __restrict__ sorted_cand, u8* stat
 }
 
 #ifdef CLODB_EMU
-// development emulation: one publish + one decide sweep over all candidates per round
-KERNEL k_wave_publish(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap,
-    u64* vmin_any, u64* vmin_src, u32 round_tag, u32 cand_total, u32* undecided_count)
+// development emulation: one publish + one decide sweep over the window list per round
+KERNEL k_wave_publish(const u32* __restrict__ list, u32 n, const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap,
+    u64* vmin_any, u64* vmin_src, u32 round_tag, u32* undecided_count)
 {
-	size_t k = GTID;
-	if (k >= cand_total || status[k] != Status_Undecided)
+	size_t i = GTID;
+	if (i >= n || status[list[i]] != Status_Undecided)
 		return;
-	wave_publish_item(u32(k), sorted_cand, cand_v0, cand_v1, remap, vmin_any, vmin_src, round_tag);
+	wave_publish_item(list[i], sorted_cand, cand_v0, cand_v1, remap, vmin_any, vmin_src, round_tag);
 	atomicAdd(undecided_count, 1u);
 }
 
-KERNEL k_wave_decide(const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, const u32* __restrict__ wedge, const u8* __restrict__ kind,
+KERNEL k_wave_decide(const u32* __restrict__ list, u32 n, const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, const u32* __restrict__ wedge, const u8* __restrict__ kind,
     const u32* __restrict__ loop, const u32* __restrict__ loopback, const Vector3* __restrict__ vpos, const u32* __restrict__ idx, const u32* __restrict__ adj_off, const u32* __restrict__ adj_corner,
-    const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked, u32 cand_total)
+    const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked)
 {
-	size_t k = GTID;
-	if (k >= cand_total || status[k] != Status_Undecided)
+	size_t i = GTID;
+	if (i >= n || status[list[i]] != Status_Undecided)
 		return;
-	wave_decide_item(u32(k), sorted_cand, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked);
+	wave_decide_item(list[i], sorted_cand, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked);
 }
 #else
 // Persistent cooperative kernel: all wavefront rounds of a pass in one launch. The undecided candidates are kept as a
 // compacted work list (double buffered, warp-aggregated appends), so a round only touches what is still undecided;
 // rounds are separated by grid-wide barriers instead of kernel launches.
-//   state[0..1] list counters (zero on entry), state[2] running round tag, state[3] rounds executed, state[4] undecided left,
+//   list[0] / state[0] hold the initial work list and its length; state[1] must be zero on entry;
+//   state[0..1] list counters, state[2] running round tag, state[3] rounds executed, state[4] undecided left,
 //   state[5] total rounds of all passes, state[6] max rounds in a pass
 struct WaveArgs
 {
@@ -1118,16 +1121,16 @@ static __global__ void __launch_bounds__(256) k_wave_rounds(WaveArgs a)
 	const u32 gsize = gridDim.x * blockDim.x;
 	const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	const u32 lane = threadIdx.x & 31;
-	u32 n = a.cand_total;
+	u32 n = *reinterpret_cast<volatile u32*>(a.state);
 	u32 tag = a.state[2];
-	const u32* cur = nullptr; // null: identity list 0..n-1
+	const u32* cur = a.list[0];
 	u32 round = 0;
-	for (;;)
+	while (n != 0)
 	{
 		++round;
 		++tag;
 		for (u32 i = gtid; i < n; i += gsize)
-			wave_publish_item(cur ? cur[i] : i, a.sorted_cand, a.cand_v0, a.cand_v1, a.remap, a.vmin_any, a.vmin_src, tag);
+			wave_publish_item(cur[i], a.sorted_cand, a.cand_v0, a.cand_v1, a.remap, a.vmin_any, a.vmin_src, tag);
 		grid.sync();
 		u32* next = a.list[round & 1];
 		u32* counter = a.state + (round & 1);
@@ -1140,7 +1143,7 @@ static __global__ void __launch_bounds__(256) k_wave_rounds(WaveArgs a)
 			bool undecided = false;
 			if (i < n)
 			{
-				k = cur ? cur[i] : i;
+				k = cur[i];
 				undecided = wave_decide_item(k, a.sorted_cand, a.status, a.cand_v0, a.cand_v1, a.remap, a.wedge, a.kind, a.loop, a.loopback, a.vpos, a.idx, a.adj_off, a.adj_corner, a.vmin_any, a.vmin_src, tag, a.collapse_remap,
 				    a.collapse_locked);
 			}
@@ -1173,6 +1176,72 @@ static __global__ void __launch_bounds__(256) k_wave_rounds(WaveArgs a)
 #endif
 
 
+
+// ---- candidate windows -------------------------------------------------------------------------------------------------
+// The serial scan of performEdgeCollapses stops long before the end of the sorted list (typically after 20-35 % of it),
+// and a candidate's fate depends only on lower-ranked candidates. So the wavefront only runs over a per-group prefix
+// window of the sorted list; if a group's stop position is not inside its window, the window is extended and the
+// wavefront continues with the new candidates (the decided ones stay decided). The result is identical to running the
+// wavefront over the whole list.
+KERNEL k_window_init(GroupState* groups, u32 G)
+{
+	size_t g = GTID;
+	if (g >= G)
+		return;
+	GroupState& gs = groups[g];
+	u32 goal = gs.tri_count > gs.target_tris ? gs.tri_count - gs.target_tris : 0;
+	u32 w = goal + goal / 8 + 64;
+	gs.win_begin = gs.cand_begin;
+	gs.win_end = gs.cand_begin + (w < gs.cand_count ? w : gs.cand_count);
+}
+
+KERNEL k_wave_window(const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_group, const GroupState* __restrict__ groups, u32* list, u32* counter, u32 cand_total)
+{
+	size_t kk = GTID;
+	bool take = false;
+	if (kk < cand_total)
+	{
+		const GroupState& gs = groups[cand_group[sorted_cand[kk]]];
+		take = u32(kk) >= gs.win_begin && u32(kk) < gs.win_end;
+	}
+#ifdef CLODB_EMU
+	if (take)
+		list[atomicAdd(counter, 1u)] = u32(kk);
+#else
+	unsigned mask = __ballot_sync(0xffffffffu, take);
+	if (mask)
+	{
+		u32 lane = threadIdx.x & 31;
+		u32 off = 0;
+		if (lane == u32(__ffs(mask) - 1))
+			off = atomicAdd(counter, u32(__popc(mask)));
+		off = __shfl_sync(0xffffffffu, off, __ffs(mask) - 1);
+		if (take)
+			list[off + __popc(mask & ((1u << lane) - 1))] = u32(kk);
+	}
+#endif
+}
+
+// after k_cut_find: groups whose stop position is not inside their window get the next window
+KERNEL k_window_check(GroupState* groups, u32 G, u32* any_extend)
+{
+	size_t g = GTID;
+	if (g >= G)
+		return;
+	GroupState& gs = groups[g];
+	if (!gs.active || gs.cand_count == 0)
+		return;
+	u32 end = gs.cand_begin + gs.cand_count;
+	if (gs.cut >= gs.win_end && gs.win_end < end)
+	{
+		u32 goal = gs.tri_count > gs.target_tris ? gs.tri_count - gs.target_tris : 0;
+		u32 grow = goal / 2 + 64;
+		gs.win_begin = gs.win_end;
+		gs.win_end = end - gs.win_end < grow ? end : gs.win_end + grow;
+		gs.cut = end;
+		atomicOr(any_extend, 1u);
+	}
+}
 
 // per sorted position: triangle weight / flip flag / tagged error for the prefix scans behind the serial early-outs
 KERNEL k_cut_inputs(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_group, const float* __restrict__ cand_error, const u8* __restrict__ kind,
@@ -1623,9 +1692,9 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 
 	dev_memset(vmin_any, 0xff, size_t(vertex_count) * 8);
 	dev_memset(vmin_src, 0xff, size_t(vertex_count) * 8);
-#ifndef CLODB_EMU
 	u32* wave_state = temp.alloc<u32>(8);
 	dev_memset(wave_state, 0, 8 * sizeof(u32));
+#ifndef CLODB_EMU
 	static u32 wave_max_blocks = 0;
 	if (!wave_max_blocks)
 	{
@@ -1666,43 +1735,70 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		dev_memset(status, 0, cand_total);
 
 		u32 rounds = 0;
-#ifdef CLODB_EMU
+		LAUNCH(k_window_init, G, groups, G);
+		u32* wave_list[2] = {tri_weight, flip_flag}; // the cut-scan inputs are not live during the rounds: reuse them as work lists
 		for (;;)
 		{
-			round_tag++;
-			rounds++;
-			dev_memset(scalars + 2, 0, sizeof(u32));
-			LAUNCH(k_wave_publish, cand_total, sort_val, status, cand_v0, cand_v1, remap, vmin_any, vmin_src, round_tag, cand_total, scalars + 2);
-			LAUNCH(k_wave_decide, cand_total, sort_val, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked, cand_total);
-			if ((rounds & 3) == 0 || rounds >= config_max_rounds())
+			// ---- wavefront over the current windows
+			dev_memset(wave_state, 0, 2 * sizeof(u32));
+			LAUNCH(k_wave_window, (size_t(cand_total) + 31) / 32 * 32, sort_val, cand_group, groups, wave_list[0], wave_state, cand_total);
+#ifdef CLODB_EMU
+			u32 listed = dev_read(wave_state);
+			for (u32 r = 0; listed != 0; )
 			{
-				u32 undecided = dev_read(scalars + 2);
-				if (undecided == 0 || rounds >= config_max_rounds())
+				round_tag++;
+				rounds++;
+				r++;
+				dev_memset(scalars + 2, 0, sizeof(u32));
+				LAUNCH(k_wave_publish, listed, wave_list[0], listed, sort_val, status, cand_v0, cand_v1, remap, vmin_any, vmin_src, round_tag, scalars + 2);
+				LAUNCH(k_wave_decide, listed, wave_list[0], listed, sort_val, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked);
+				if (dev_read(scalars + 2) == 0 || r >= config_max_rounds())
 					break;
 			}
-		}
 #else
-		{
-			WaveArgs wa;
-			wa.sorted_cand = sort_val, wa.status = status, wa.cand_v0 = cand_v0, wa.cand_v1 = cand_v1, wa.remap = remap, wa.wedge = wedge, wa.kind = kind, wa.loop = loop, wa.loopback = loopback;
-			wa.vpos = vpos, wa.idx = idx, wa.adj_off = adj_off, wa.adj_corner = adj_corner, wa.vmin_any = vmin_any, wa.vmin_src = vmin_src, wa.collapse_remap = collapse_remap, wa.collapse_locked = collapse_locked;
-			wa.list[0] = tri_weight; // the cut-scan inputs are not live during the rounds: reuse them as the two work lists
-			wa.list[1] = flip_flag;
-			wa.state = wave_state;
-			wa.cand_total = cand_total, wa.max_rounds = config_max_rounds();
-			dev_memset(wave_state, 0, 2 * sizeof(u32));
-			u32 blocks = std::min<u32>(wave_max_blocks, (cand_total + 255) / 256);
-			LAUNCH_COOP(k_wave_rounds, blocks, 256, wa);
-		}
+			{
+				WaveArgs wa;
+				wa.sorted_cand = sort_val, wa.status = status, wa.cand_v0 = cand_v0, wa.cand_v1 = cand_v1, wa.remap = remap, wa.wedge = wedge, wa.kind = kind, wa.loop = loop, wa.loopback = loopback;
+				wa.vpos = vpos, wa.idx = idx, wa.adj_off = adj_off, wa.adj_corner = adj_corner, wa.vmin_any = vmin_any, wa.vmin_src = vmin_src, wa.collapse_remap = collapse_remap, wa.collapse_locked = collapse_locked;
+				wa.list[0] = wave_list[0];
+				wa.list[1] = wave_list[1];
+				wa.state = wave_state;
+				wa.cand_total = cand_total, wa.max_rounds = config_max_rounds();
+				u32 blocks = std::min<u32>(wave_max_blocks, (cand_total + 255) / 256);
+				LAUNCH_COOP(k_wave_rounds, blocks, 256, wa);
+			}
 #endif
+
+			// ---- where would the serial scan have stopped?
+			LAUNCH(k_cut_inputs, cand_total, sort_val, status, cand_v0, cand_group, cand_error, kind, tri_weight, flip_flag, tagged_error, cand_total);
+			exclusive_scan_u32(tri_weight, tri_weight, cand_total, nullptr, temp);
+			exclusive_scan_u32(flip_flag, flip_flag, cand_total, nullptr, temp);
+			exclusive_scan<u64, OpMaxU64>(tagged_error, tagged_error, cand_total, nullptr, temp);
+			LAUNCH(k_cut_find, cand_total, sort_val, status, cand_group, cand_error, groups, tri_weight, flip_flag, tagged_error, cand_total);
+			dev_memset(scalars + 3, 0, sizeof(u32));
+			LAUNCH(k_window_check, G, groups, G, scalars + 3);
+			if (dev_read(scalars + 3) == 0)
+				break;
+			g_simplify_stats.window_extensions++;
+		}
+#ifdef CLODB_EMU
 		g_simplify_stats.rounds += rounds;
 		g_simplify_stats.max_rounds = std::max(g_simplify_stats.max_rounds, rounds);
-
-		LAUNCH(k_cut_inputs, cand_total, sort_val, status, cand_v0, cand_group, cand_error, kind, tri_weight, flip_flag, tagged_error, cand_total);
-		exclusive_scan_u32(tri_weight, tri_weight, cand_total, nullptr, temp);
-		exclusive_scan_u32(flip_flag, flip_flag, cand_total, nullptr, temp);
-		exclusive_scan<u64, OpMaxU64>(tagged_error, tagged_error, cand_total, nullptr, temp);
-		LAUNCH(k_cut_find, cand_total, sort_val, status, cand_group, cand_error, groups, tri_weight, flip_flag, tagged_error, cand_total);
+#endif
+		if (getenv("CLODB200_DEBUG_CUT"))
+		{
+			std::vector<GroupState> gh = dev_download(groups, G);
+			double scanned = 0, total = 0, window = 0;
+			for (u32 g = 0; g < G; ++g)
+				if (gh[g].active && gh[g].cand_count)
+				{
+					u32 cut = std::min(gh[g].cut, gh[g].cand_begin + gh[g].cand_count);
+					scanned += cut - gh[g].cand_begin;
+					window += gh[g].win_end - gh[g].cand_begin;
+					total += gh[g].cand_count;
+				}
+			fprintf(stderr, "pass %u: T %u cands %u scanned %.0f (%.1f%%) window %.0f rounds %u ext %u\n", g_simplify_stats.passes, cur_T, cand_total, scanned, total ? 100.0 * scanned / total : 0.0, window, rounds, g_simplify_stats.window_extensions);
+		}
 		dev_memset(group_collapses, 0, size_t(G) * 4);
 		dev_memset(group_error_bits, 0, size_t(G) * 4);
 		LAUNCH(k_cut_apply, cand_total, sort_val, status, cand_v0, cand_group, cand_error, wedge, kind, groups, group_collapses, group_error_bits, collapse_remap, cand_total);
