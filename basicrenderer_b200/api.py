@@ -245,7 +245,7 @@ class ClodLib:
         for name, dtype in _RECORD_DTYPES.items():
             ptr, size = C.c_void_p(), C.c_size_t()
             self._lib.clodb200_recordGet(handle, name.encode(), C.byref(ptr), C.byref(size))
-            arrays[name] = np.frombuffer(C.string_at(ptr, size.value), dtype=dtype).copy() if size.value else np.zeros(0, dtype)
+            arrays[name] = np.frombuffer((C.c_ubyte * size.value).from_address(ptr.value), dtype=dtype).copy() if size.value else np.zeros(0, dtype)
         self._lib.clodb200_recordFree(handle)
         return DagRecord(arrays)
 

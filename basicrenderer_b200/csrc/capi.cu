@@ -126,23 +126,49 @@ struct RecordSink : DagSink
 	u32 cluster_total = 0;
 	u64 index_total = 0;
 
+	typedef std::vector<unsigned char> Blob;
+	Blob *b_depth = nullptr, *b_simplified, *b_refined, *b_bounds, *b_vcount, *b_indices, *b_ioffsets, *b_goffsets;
+
+	template <typename T>
+	static void put(Blob* b, const T* data, size_t count)
+	{
+		const unsigned char* p = reinterpret_cast<const unsigned char*>(data);
+		b->insert(b->end(), p, p + count * sizeof(T));
+	}
+
+	// index_hint: expected total index count of the stream (about 2x the input), reserved up front
+	void bind(size_t index_hint)
+	{
+		b_depth = &rec->blobs["group_depth"];
+		b_simplified = &rec->blobs["group_simplified"];
+		b_refined = &rec->blobs["cluster_refined"];
+		b_bounds = &rec->blobs["cluster_bounds"];
+		b_vcount = &rec->blobs["cluster_vertex_count"];
+		b_indices = &rec->blobs["cluster_indices"];
+		b_ioffsets = &rec->blobs["cluster_index_offsets"];
+		b_goffsets = &rec->blobs["group_cluster_offsets"];
+		if (keep_indices)
+			b_indices->reserve(index_hint * 4);
+	}
+
 	int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t) override
 	{
-		rec->push<int>("group_depth", group.depth);
-		rec->append<float>("group_simplified", group.simplified, 5);
+		put(b_depth, &group.depth, 1);
+		put(b_simplified, group.simplified, 5);
 		for (size_t i = 0; i < cluster_count; ++i)
 		{
 			const DagCluster& c = clusters[i];
-			rec->push<int>("cluster_refined", c.refined);
-			rec->append<float>("cluster_bounds", c.bounds, 5);
-			rec->push<u32>("cluster_vertex_count", u32(c.vertex_count));
+			put(b_refined, &c.refined, 1);
+			put(b_bounds, c.bounds, 5);
+			u32 vc = u32(c.vertex_count);
+			put(b_vcount, &vc, 1);
 			if (keep_indices)
-				rec->append<unsigned int>("cluster_indices", c.indices, c.index_count);
+				put(b_indices, c.indices, c.index_count);
 			index_total += c.index_count;
-			rec->push<u64>("cluster_index_offsets", index_total);
+			put(b_ioffsets, &index_total, 1);
 		}
 		cluster_total += u32(cluster_count);
-		rec->push<u32>("group_cluster_offsets", cluster_total);
+		put(b_goffsets, &cluster_total, 1);
 		return next_group++;
 	}
 };
@@ -193,6 +219,7 @@ void clodb200_shutdown(void)
 		return;
 	g_ws.persist.destroy();
 	g_ws.temp.destroy();
+	g_ws.stage.destroy();
 #ifndef CLODB_EMU
 	cudaStreamDestroy(g_stream);
 	g_stream = 0;
@@ -409,6 +436,13 @@ int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* i
 	});
 }
 
+KERNEL k_index_range(const u32* __restrict__ indices, size_t n, u32 vertex_count, u32* bad)
+{
+	size_t i = GTID;
+	if (i < n && indices[i] >= vertex_count)
+		atomicOr(bad, 1u);
+}
+
 struct clodb200_device_mesh
 {
 	DeviceMesh mesh;
@@ -441,9 +475,6 @@ static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
 {
 	if (mesh.index_count % 3 || mesh.vertex_positions_stride % 4 || mesh.vertex_attributes_stride % 4 || mesh.attribute_count > 32)
 		throw Error("clodb200: index count must be a multiple of 3, strides multiples of 4, at most 32 attributes");
-	for (size_t i = 0; i < mesh.index_count; ++i)
-		if (mesh.indices[i] >= mesh.vertex_count)
-			throw Error("clodb200: index out of range");
 	clodb200_device_mesh* dm = new clodb200_device_mesh();
 	try
 	{
@@ -487,6 +518,13 @@ static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
 		dm->allocations.push_back(dm->indices);
 		dev_h2d(dm->indices, mesh.indices, mesh.index_count * 4);
 		dm->index_count = mesh.index_count;
+		// range check on the device copy (the reference asserts; a bad index would read out of bounds in every stage)
+		u32* bad = static_cast<u32*>(dev_malloc(sizeof(u32)));
+		dm->allocations.push_back(bad);
+		dev_memset(bad, 0, sizeof(u32));
+		LAUNCH(k_index_range, mesh.index_count, dm->indices, mesh.index_count, u32(V), bad);
+		if (dev_read(bad))
+			throw Error("clodb200: index out of range");
 	}
 	catch (...)
 	{
@@ -625,6 +663,7 @@ static clodb200_record* record_build(const clodb200_config& config, const clodb2
 		sink.keep_indices = keep_indices;
 		rec->push<u32>("group_cluster_offsets", 0);
 		rec->push<u64>("cluster_index_offsets", 0);
+		sink.bind(dm->index_count * 2 + dm->index_count / 8);
 		size_t clusters = build_locked(config, dm, sink);
 		const BuildStats& st = g_last_build_stats;
 		rec->append<u32>("level_triangles", st.level_triangles.data(), st.level_triangles.size());

@@ -47,6 +47,7 @@ struct Workspace
 {
 	Arena persist; // level outputs, kept until the build finishes
 	Arena temp;    // stage temporaries, stack discipline
+	HostStage stage; // pinned host buffer receiving each level's cluster tables for the output callbacks
 };
 
 // ---- S1: position remap + protect bits (remap.cu) ----------------------------------------------------------------

@@ -360,6 +360,13 @@ static void seg_area_scan(const Box* boxes, const u32* order, const u32* node_of
 		out_area[p] = box_area_merge(mn, mx, boxes[order[p]]);
 	}
 }
+
+static void seg_area_scan_all(const Box* boxes, u32* const* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* areas, u32 T, Arena& temp)
+{
+	for (int k = 0; k < 3; ++k)
+		for (int b = 0; b < 2; ++b)
+			seg_area_scan(boxes, order[k], node_of_pos, node_begin, node_count, areas + size_t(k * 2 + b) * (size_t(T) + 1), T, b != 0, temp);
+}
 #else
 struct ScanElem
 {
@@ -467,12 +474,24 @@ struct OpSegBox
 
 // Segmented inclusive min/max scan of the triangle boxes along one axis order -> surface area at every position, in one
 // chained pass (prims.cuh): per element it reads order u32 + node id u32 + the gathered 32-byte box and writes one f32.
-static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count,
-    float* out_area, u32 T, int backward, u32* chain_flags, char* chain_aggregate, char* chain_inclusive, u32 epoch)
+struct SweepArgs
+{
+	const u32* order[3];
+	float* area; // 6 arrays of T + 1 floats: [axis * 2 + backward]
+};
+
+// All six sweeps of a tree level (3 axis orders x forward/backward) in one launch: blockIdx.x = tile * 6 + sweep, so the six
+// independent tile chains advance concurrently and hide each other's look-back latency.
+static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __restrict__ boxes, SweepArgs sw, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count,
+    u32 T, u32 tiles, u32* chain_flags, char* chain_aggregate, char* chain_inclusive, u32 epoch)
 {
 	__shared__ ScanElem smem[SA_THREADS / 32];
 	__shared__ ScanElem s_prefix;
-	u32 base = blockIdx.x * SA_TILE + threadIdx.x * SA_ITEMS;
+	const u32 sweep = blockIdx.x % 6, tile = blockIdx.x / 6;
+	const int backward = sweep & 1;
+	const u32* __restrict__ order = sw.order[sweep >> 1];
+	float* out_area = sw.area + size_t(sweep) * (size_t(T) + 1);
+	u32 base = tile * SA_TILE + threadIdx.x * SA_ITEMS;
 	ScanElem e[SA_ITEMS];
 	ScanElem agg = scan_identity();
 #pragma unroll
@@ -485,7 +504,8 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 	ScanElem ex = block_scan_exclusive(agg, smem, &total);
 	if (threadIdx.x < 32)
 	{
-		ScanElem prefix = scan_chain_lookback<ScanElem, OpSegBox>(blockIdx.x, total, chain_flags, chain_aggregate, chain_inclusive, epoch);
+		size_t region = size_t(sweep) * tiles;
+		ScanElem prefix = scan_chain_lookback<ScanElem, OpSegBox>(tile, total, chain_flags + region, chain_aggregate + region * SCAN_CHAIN_VALUE_BYTES, chain_inclusive + region * SCAN_CHAIN_VALUE_BYTES, epoch);
 		if (threadIdx.x == 0)
 			s_prefix = prefix;
 	}
@@ -505,21 +525,30 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 	}
 }
 
-static void seg_area_scan(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* out_area, u32 T, bool backward, Arena&)
+// areas: 6 arrays of T + 1 floats, [axis * 2 + backward]
+static void seg_area_scan_all(const Box* boxes, u32* const* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* areas, u32 T, Arena&)
 {
 	u32 tiles = (T + SA_TILE - 1) / SA_TILE;
-	scan_chain_reserve(tiles);
+	scan_chain_reserve(size_t(tiles) * 6);
 	u32 epoch = scan_chain_next_epoch();
-	LAUNCH_GRID(k_sa_chained, tiles, SA_THREADS, boxes, order, node_of_pos, node_begin, node_count, out_area, T, backward ? 1 : 0, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch);
+	SweepArgs sw;
+	for (int k = 0; k < 3; ++k)
+		sw.order[k] = order[k];
+	sw.area = areas;
+	LAUNCH_GRID(k_sa_chained, size_t(tiles) * 6, SA_THREADS, boxes, sw, node_of_pos, node_begin, node_count, T, tiles, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch);
 }
 #endif
 
 // (cost, axis, index) argmin per large node (bvhPivot over count > max_triangles, vertices == NULL)
-KERNEL k_pivot_large(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const float* __restrict__ larea, const float* __restrict__ rarea, u64* node_best, u32 T, int axis, SplitParams sp)
+KERNEL k_pivot_large(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const float* __restrict__ areas, u64* node_best, u32 T, SplitParams sp)
 {
-	size_t p = GTID;
-	if (p >= T)
+	size_t gi = GTID;
+	if (gi >= size_t(T) * 3)
 		return;
+	int axis = int(gi / T);
+	size_t p = gi - size_t(axis) * T;
+	const float* larea = areas + size_t(axis * 2) * (size_t(T) + 1);
+	const float* rarea = areas + size_t(axis * 2 + 1) * (size_t(T) + 1);
 	u32 n = node_of_pos[p];
 	if (n == NODE_DONE)
 		return;
@@ -954,8 +983,7 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 	u32* node_of_pos_alt = temp.alloc<u32>(T);
 	u8* boundary = temp.alloc<u8>(T);
 	u8* side = temp.alloc<u8>(T);
-	float* larea = temp.alloc<float>(size_t(T) + 1);
-	float* rarea = temp.alloc<float>(size_t(T) + 1);
+	float* areas = temp.alloc<float>((size_t(T) + 1) * 6); // prefix / suffix surface areas of the three axis orders
 	u32* flags3 = temp.alloc<u32>(size_t(T) * 3);
 
 	LAUNCH(k_init_nodes, S, seg_offsets, S, node_begin, node_count, node_of_pos);
@@ -979,12 +1007,8 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 
 		if (any_large)
 		{
-			for (int k = 0; k < 3; ++k)
-			{
-				seg_area_scan(boxes, order[k], node_of_pos, node_begin, node_count, larea, T, false, temp);
-				seg_area_scan(boxes, order[k], node_of_pos, node_begin, node_count, rarea, T, true, temp);
-				LAUNCH(k_pivot_large, T, node_of_pos, node_begin, node_count, larea, rarea, node_best, T, k, sp);
-			}
+			seg_area_scan_all(boxes, order, node_of_pos, node_begin, node_count, areas, T, temp);
+			LAUNCH(k_pivot_large, size_t(T) * 3, node_of_pos, node_begin, node_count, areas, node_best, T, sp);
 			LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 1);
 		}
 		LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 0);

@@ -63,14 +63,40 @@ KERNEL k_copy_segments(const u32* __restrict__ src_tri, const u32* __restrict__ 
 	dst_tri[t * 3 + 2] = src_tri[src * 3 + 2];
 }
 
-static size_t emit_level(const ClusterSet& cs, const std::vector<int>& refined, const std::vector<float>& bounds5, const std::vector<float>& precise4, const Config& config,
+// Host view of one level's cluster tables inside the pinned staging buffer (filled by an asynchronous copy that is
+// enqueued right after the level is clusterized, so it overlaps the level's partition / simplification kernels).
+struct LevelHost
+{
+	const u32* tri = nullptr;
+	const u32* off = nullptr;
+	const u32* vcount = nullptr;
+};
+
+static LevelHost download_level_async(const ClusterSet& cs, Workspace& ws, BuildStats& stats)
+{
+	size_t tri_bytes = size_t(cs.triangle_count) * 12, off_bytes = (size_t(cs.cluster_count) + 1) * 4, vc_bytes = size_t(cs.cluster_count) * 4;
+	size_t off_at = (tri_bytes + 255) & ~size_t(255), vc_at = (off_at + off_bytes + 255) & ~size_t(255);
+	ws.stage.reserve(vc_at + vc_bytes + 256);
+	char* base = ws.stage.base;
+	dev_d2h_async(base, cs.tri, tri_bytes);
+	dev_d2h_async(base + off_at, cs.cluster_tri_offset, off_bytes);
+	dev_d2h_async(base + vc_at, cs.cluster_vertex_count, vc_bytes);
+	stats.d2h_bytes += tri_bytes + off_bytes + vc_bytes;
+	LevelHost h;
+	h.tri = reinterpret_cast<const u32*>(base);
+	h.off = reinterpret_cast<const u32*>(base + off_at);
+	h.vcount = reinterpret_cast<const u32*>(base + vc_at);
+	return h;
+}
+
+static size_t emit_level(const ClusterSet& cs, const LevelHost& host, const std::vector<int>& refined, const std::vector<float>& bounds5, const std::vector<float>& precise4, const Config& config,
     const GroupSet& groups, const std::vector<u32>& group_clusters, const std::vector<float>& group_bounds5, int depth, DagSink& sink, std::vector<int>& group_ids, BuildStats& stats)
 {
-	// host copies of the level's cluster tables
-	std::vector<u32> tri = dev_download(cs.tri, size_t(cs.triangle_count) * 3);
-	std::vector<u32> off = dev_download(cs.cluster_tri_offset, size_t(cs.cluster_count) + 1);
-	std::vector<u32> vcount = dev_download(cs.cluster_vertex_count, cs.cluster_count);
-	stats.d2h_bytes += tri.size() * 4 + off.size() * 4 + vcount.size() * 4;
+	// the level's cluster tables were sent to the pinned staging buffer when the level was built
+	dev_d2h_async_wait();
+	const u32* tri = host.tri;
+	const u32* off = host.off;
+	const u32* vcount = host.vcount;
 
 	std::vector<DagCluster> out;
 	group_ids.assign(groups.group_count, -1);
@@ -91,7 +117,7 @@ static size_t emit_level(const ClusterSet& cs, const std::vector<int>& refined, 
 			dc.bounds[2] = src[2];
 			dc.bounds[3] = src[3];
 			dc.bounds[4] = bounds5[size_t(c) * 5 + 4];
-			dc.indices = tri.data() + size_t(off[c]) * 3;
+			dc.indices = tri + size_t(off[c]) * 3;
 			dc.index_count = size_t(off[c + 1] - off[c]) * 3;
 			dc.vertex_count = vcount[c];
 		}
@@ -122,6 +148,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 	// initial clusterization + precise bounds (clusterlod.h:844-848)
 	u32 seg0[2] = {0, T0};
 	ClusterSet level = clusterize(indices_dev, T0, seg0, 1, mesh.positions, config, ws);
+	LevelHost level_host = download_level_async(level, ws, stats);
 	size_t total_clusters = level.cluster_count;
 
 	float* bounds4 = persist.alloc<float>(size_t(level.cluster_count) * 4);
@@ -201,7 +228,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 			precise4.assign(size_t(K) * 4, 0.f);
 
 		std::vector<int> group_ids;
-		emit_level(level, refined_host, bounds5_host, precise4, config, groups, group_clusters_host, group_bounds5, depth, sink, group_ids, stats);
+		emit_level(level, level_host, refined_host, bounds5_host, precise4, config, groups, group_clusters_host, group_bounds5, depth, sink, group_ids, stats);
 
 		// segments for re-clusterization: simplified lists of non-terminal groups
 		std::vector<u32> seg_src, seg_dst(1, 0);
@@ -240,6 +267,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		}
 
 		ClusterSet next = clusterize(next_tri, T_next, seg_dst.data(), S, mesh.positions, config, ws);
+		level_host = download_level_async(next, ws, stats);
 		total_clusters += next.cluster_count;
 
 		// clusters inherit the refined id and the bounds of the group they came from (clusterlod.h:919-925)
@@ -280,7 +308,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 			precise4 = dev_download(p4, 4);
 		}
 		std::vector<int> ids;
-		emit_level(level, refined_host, b5, precise4, config, last, gc, gb5, depth, sink, ids, stats);
+		emit_level(level, level_host, refined_host, b5, precise4, config, last, gc, gb5, depth, sink, ids, stats);
 	}
 
 	stats.total_clusters = total_clusters;

@@ -45,7 +45,76 @@ void dev_d2d(void* dst, const void* src, size_t bytes)
 void dev_sync()
 {
 }
+void HostStage::reserve(size_t bytes)
+{
+	if (bytes <= capacity)
+		return;
+	free(base);
+	base = static_cast<char*>(malloc(bytes));
+	capacity = bytes;
+}
+void HostStage::destroy()
+{
+	free(base);
+	base = nullptr;
+	capacity = 0;
+}
+void dev_d2h_async(void* dst, const void* src, size_t bytes)
+{
+	memcpy(dst, src, bytes);
+}
+void dev_d2h_async_wait()
+{
+}
 #else
+namespace
+{
+cudaStream_t g_copy_stream = nullptr;
+cudaEvent_t g_copy_ready = nullptr, g_copy_done = nullptr;
+void ensure_copy_stream()
+{
+	if (g_copy_stream)
+		return;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+	CUDA_CHECK(cudaEventCreateWithFlags(&g_copy_ready, cudaEventDisableTiming));
+	CUDA_CHECK(cudaEventCreateWithFlags(&g_copy_done, cudaEventDisableTiming));
+}
+} // namespace
+void HostStage::reserve(size_t bytes)
+{
+	if (bytes <= capacity)
+		return;
+	dev_d2h_async_wait();
+	if (base)
+		cudaFreeHost(base);
+	base = nullptr;
+	size_t cap = bytes + bytes / 4;
+	CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&base), cap, cudaHostAllocDefault));
+	capacity = cap;
+}
+void HostStage::destroy()
+{
+	if (base)
+		cudaFreeHost(base);
+	base = nullptr;
+	capacity = 0;
+}
+void dev_d2h_async(void* dst, const void* src, size_t bytes)
+{
+	if (!bytes)
+		return;
+	ensure_copy_stream();
+	CUDA_CHECK(cudaEventRecord(g_copy_ready, g_stream));
+	CUDA_CHECK(cudaStreamWaitEvent(g_copy_stream, g_copy_ready, 0));
+	CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_copy_stream));
+	CUDA_CHECK(cudaEventRecord(g_copy_done, g_copy_stream));
+}
+void dev_d2h_async_wait()
+{
+	if (g_copy_stream)
+		CUDA_CHECK(cudaStreamSynchronize(g_copy_stream));
+}
+
 void* dev_malloc(size_t bytes)
 {
 	void* p = nullptr;

@@ -228,6 +228,19 @@ void dev_d2h(void* dst, const void* src, size_t bytes);
 void dev_d2d(void* dst, const void* src, size_t bytes);
 void dev_sync();
 
+// ---- pinned host staging + copy stream: level outputs are downloaded asynchronously while the build stream keeps working
+struct HostStage
+{
+	char* base = nullptr;
+	size_t capacity = 0;
+	void reserve(size_t bytes); // grows (never shrinks); contents are not preserved
+	void destroy();
+};
+// Enqueues dst_host <- src_dev on the copy stream once everything issued so far on the build stream has finished.
+void dev_d2h_async(void* dst_host_pinned, const void* src, size_t bytes);
+// Blocks the host until every dev_d2h_async issued so far has landed.
+void dev_d2h_async_wait();
+
 // ---- stack arena: all per-build temporaries come from one cudaMalloc'd slab (no allocator calls inside the loop) -----
 struct Arena
 {

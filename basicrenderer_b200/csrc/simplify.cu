@@ -1092,6 +1092,87 @@ KERNEL k_wave_decide(const u32* __restrict__ list, u32 n, const u32* __restrict_
 	wave_decide_item(list[i], sorted_cand, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked);
 }
 #else
+// Same step as wave_decide_item, executed by 8 cooperating lanes (gmask) per candidate: the two walks over the adjacency of
+// r0 are split across the lanes, which shortens the dependent-load chain of a round from ~50 to ~10 memory latencies. All 8
+// lanes pass the same k and receive the same result.
+DEVFN bool wave_decide_coop8(u32 k, bool valid, unsigned gmask, u32 lane8, const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap,
+    const u32* __restrict__ wedge, const u8* __restrict__ kind, const u32* __restrict__ loop, const u32* __restrict__ loopback, const Vector3* __restrict__ vpos, const u32* __restrict__ idx, const u32* __restrict__ adj_off,
+    const u32* __restrict__ adj_corner, const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked)
+{
+	if (!valid)
+		return false;
+	u32 c = sorted_cand[k];
+	u32 i0 = cand_v0[c], i1 = cand_v1[c];
+	u32 r0 = remap[i0], r1 = remap[i1];
+	if (collapse_locked[r0] | collapse_locked[r1])
+	{
+		if (lane8 == 0)
+			status[k] = Status_Locked;
+		return false;
+	}
+	if (wave_min(vmin_any, r0, round_tag) != k || wave_min(vmin_any, r1, round_tag) != k)
+		return true;
+	u32 begin = adj_off[r0], end = adj_off[r0 + 1];
+	bool wait = false;
+	for (u32 e = begin + lane8; e < end; e += 8)
+	{
+		u32 corner = adj_corner[e];
+		u32 a = remap[idx[corner_next(corner)]], b = remap[idx[corner_prev(corner)]];
+		wait |= wave_min(vmin_src, a, round_tag) < k || wave_min(vmin_src, b, round_tag) < k;
+	}
+	if (__ballot_sync(gmask, wait))
+		return true;
+	bool flip = false;
+	{
+		const Vector3 v0 = vpos[r0];
+		const Vector3 v1 = vpos[r1];
+		for (u32 e = begin + lane8; e < end; e += 8)
+		{
+			u32 corner = adj_corner[e];
+			u32 a = collapse_remap[remap[idx[corner_next(corner)]]];
+			u32 b = collapse_remap[remap[idx[corner_prev(corner)]]];
+			if (a == r1 || b == r1 || a == b)
+				continue;
+			flip |= has_triangle_flip(vpos[a], vpos[b], v0, v1);
+		}
+	}
+	if (__ballot_sync(gmask, flip))
+	{
+		if (lane8 == 0)
+			status[k] = Status_Flip;
+		return false;
+	}
+	if (lane8 == 0)
+	{
+		u8 kd = kind[i0];
+		if (kd == Kind_Complex)
+		{
+			u32 v = i0;
+			do
+			{
+				collapse_remap[v] = get_complex_target(v, i1, remap, loop, loopback);
+				v = wedge[v];
+			} while (v != i0);
+		}
+		else if (kd == Kind_Seam)
+		{
+			u32 s0 = wedge[i0];
+			u32 s1 = loop[i0] == i1 ? loopback[s0] : loop[s0];
+			s1 = (s1 != NONE) ? s1 : wedge[i1];
+			collapse_remap[i0] = i1;
+			collapse_remap[s0] = s1;
+		}
+		else
+		{
+			collapse_remap[i0] = i1;
+		}
+		collapse_locked[r0] = 1;
+		collapse_locked[r1] = 1;
+		status[k] = Status_Performed;
+	}
+	return false;
+}
+
 // Persistent cooperative kernel: all wavefront rounds of a pass in one launch. The undecided candidates are kept as a
 // compacted work list (double buffered, warp-aggregated appends), so a round only touches what is still undecided;
 // rounds are separated by grid-wide barriers instead of kernel launches.
@@ -1113,9 +1194,11 @@ struct WaveArgs
 	u32* list[2];
 	u32* state;
 	u32 cand_total, max_rounds;
+	u32* round_log; // optional (debug): per round {active count, globaltimer ns low word at round end}
 };
 
-static __global__ void __launch_bounds__(256) k_wave_rounds(WaveArgs a)
+static const int WAVE_THREADS = 1024; // one CTA per SM: the grid barrier costs one atomic per CTA
+static __global__ void __launch_bounds__(WAVE_THREADS, 1) k_wave_rounds(WaveArgs a)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const u32 gsize = gridDim.x * blockDim.x;
@@ -1136,29 +1219,36 @@ static __global__ void __launch_bounds__(256) k_wave_rounds(WaveArgs a)
 		u32* counter = a.state + (round & 1);
 		if (gtid == 0)
 			a.state[(round + 1) & 1] = 0;
-		for (u32 base = gtid - lane; base < n; base += gsize)
+		const u32 sub = lane >> 3, lane8 = lane & 7;
+		const unsigned gmask = 0xffu << (sub * 8);
+		for (u32 base = (gtid >> 5) * 4; base < n; base += (gsize >> 5) * 4)
 		{
-			u32 i = base + lane;
-			u32 k = 0;
-			bool undecided = false;
-			if (i < n)
-			{
-				k = cur[i];
-				undecided = wave_decide_item(k, a.sorted_cand, a.status, a.cand_v0, a.cand_v1, a.remap, a.wedge, a.kind, a.loop, a.loopback, a.vpos, a.idx, a.adj_off, a.adj_corner, a.vmin_any, a.vmin_src, tag, a.collapse_remap,
-				    a.collapse_locked);
-			}
-			unsigned mask = __ballot_sync(0xffffffffu, undecided);
+			u32 i = base + sub;
+			bool valid = i < n;
+			u32 k = valid ? cur[i] : 0;
+			bool undecided = wave_decide_coop8(k, valid, gmask, lane8, a.sorted_cand, a.status, a.cand_v0, a.cand_v1, a.remap, a.wedge, a.kind, a.loop, a.loopback, a.vpos, a.idx, a.adj_off, a.adj_corner, a.vmin_any, a.vmin_src, tag,
+			    a.collapse_remap, a.collapse_locked);
+			__syncwarp();
+			unsigned mask = __ballot_sync(0xffffffffu, undecided && lane8 == 0);
 			if (mask)
 			{
+				int leader = __ffs(mask) - 1;
 				u32 off = 0;
-				if (lane == 0)
+				if (int(lane) == leader)
 					off = atomicAdd(counter, u32(__popc(mask)));
-				off = __shfl_sync(0xffffffffu, off, 0);
-				if (undecided)
+				off = __shfl_sync(0xffffffffu, off, leader);
+				if (undecided && lane8 == 0)
 					next[off + __popc(mask & ((1u << lane) - 1))] = k;
 			}
 		}
 		grid.sync();
+		if (a.round_log && gtid == 0 && round < 256)
+		{
+			unsigned long long t;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+			a.round_log[round * 2] = n;
+			a.round_log[round * 2 + 1] = u32(t);
+		}
 		n = *reinterpret_cast<volatile u32*>(counter);
 		if (n == 0 || round >= a.max_rounds)
 			break;
@@ -1699,7 +1789,7 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 	if (!wave_max_blocks)
 	{
 		int per_sm = 0, device = 0, sms = 0;
-		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wave_rounds, 256, 0));
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wave_rounds, WAVE_THREADS, 0));
 		CUDA_CHECK(cudaGetDevice(&device));
 		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
 		wave_max_blocks = u32(std::max(1, per_sm) * sms);
@@ -1764,8 +1854,24 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 				wa.list[1] = wave_list[1];
 				wa.state = wave_state;
 				wa.cand_total = cand_total, wa.max_rounds = config_max_rounds();
-				u32 blocks = std::min<u32>(wave_max_blocks, (cand_total + 255) / 256);
-				LAUNCH_COOP(k_wave_rounds, blocks, 256, wa);
+				static const bool log_rounds = getenv("CLODB200_DEBUG_ROUNDS") != nullptr;
+				wa.round_log = nullptr;
+				if (log_rounds)
+				{
+					wa.round_log = temp.alloc<u32>(512);
+					dev_memset(wa.round_log, 0, 512 * 4);
+				}
+				static const u32 blocks_per_sm_cap = getenv("CLODB200_WAVE_BLOCKS") ? u32(atoi(getenv("CLODB200_WAVE_BLOCKS"))) : 0u;
+				u32 blocks = std::min<u32>(blocks_per_sm_cap ? std::min(wave_max_blocks, blocks_per_sm_cap) : wave_max_blocks, (cand_total + WAVE_THREADS / 8 - 1) / (WAVE_THREADS / 8));
+				LAUNCH_COOP(k_wave_rounds, blocks, WAVE_THREADS, wa);
+				if (log_rounds)
+				{
+					std::vector<u32> lg = dev_download(wa.round_log, 512);
+					fprintf(stderr, "wave T %u cands %u blocks %u:", cur_T, cand_total, blocks);
+					for (u32 r = 1; r < 256 && lg[r * 2]; ++r)
+						fprintf(stderr, " %u/%.0fus", lg[r * 2], r > 1 ? (lg[r * 2 + 1] - lg[r * 2 - 1]) / 1e3 : 0.0);
+					fprintf(stderr, "\n");
+				}
 			}
 #endif
 
