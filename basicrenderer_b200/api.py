@@ -181,6 +181,28 @@ class ClodLib:
         return out
 
 
+    def local_indices(self, indices: np.ndarray):
+        """clodLocalIndices for one cluster -> (vertices[unique], triangles u8[len(indices)])"""
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        vertices = np.zeros(max(1, indices.size), dtype=np.uint32)
+        triangles = np.zeros(indices.size, dtype=np.uint8)
+        self._lib.clodb200_localIndices.restype = C.c_size_t
+        n = self._lib.clodb200_localIndices(_ptr(vertices), _ptr(triangles), _ptr(indices), C.c_size_t(indices.size))
+        if n == 0 and indices.size:
+            raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200_localIndices failed")
+        return vertices[:n].copy(), triangles
+
+    def local_indices_batch(self, indices: np.ndarray, cluster_index_offsets: np.ndarray, vertex_capacity: int = 128):
+        """-> (vertices[K, vertex_capacity], triangles u8[len(indices)], vertex_counts[K])"""
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        offs = np.ascontiguousarray(cluster_index_offsets, dtype=np.uint64)
+        K = offs.size - 1
+        vertices = np.zeros((K, vertex_capacity), dtype=np.uint32)
+        triangles = np.zeros(indices.size, dtype=np.uint8)
+        counts = np.zeros(K, dtype=np.uint32)
+        self._check(self._lib.clodb200_localIndicesBatch(_ptr(indices), _ptr(offs), C.c_size_t(K), C.c_size_t(vertex_capacity), _ptr(vertices), _ptr(triangles), _ptr(counts)))
+        return vertices, triangles, counts
+
     def lock_boundary(self, locks: np.ndarray, indices: np.ndarray, group_index_offsets: np.ndarray, remap: np.ndarray, vertex_lock=None) -> np.ndarray:
         locks = np.ascontiguousarray(locks, dtype=np.uint8).copy()
         indices = np.ascontiguousarray(indices, dtype=np.uint32)

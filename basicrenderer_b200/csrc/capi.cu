@@ -377,6 +377,48 @@ int clodb200_lockBoundary(unsigned char* locks, const unsigned int* indices, con
 	});
 }
 
+int clodb200_localIndicesBatch(const unsigned int* indices, const uint64_t* cluster_index_offsets, size_t cluster_count, size_t vertex_capacity,
+    unsigned int* out_vertices, unsigned char* out_triangles, unsigned int* out_vertex_counts)
+{
+	return guarded([&]() -> int {
+		if (cluster_count == 0)
+			return CLODB200_OK;
+		if (!indices || !cluster_index_offsets || !out_vertices || !out_triangles || !out_vertex_counts || vertex_capacity == 0 || vertex_capacity > 256)
+			return fail(CLODB200_ERR_INVALID, "clodb200_localIndicesBatch: invalid arguments");
+		size_t index_count = size_t(cluster_index_offsets[cluster_count]);
+		for (size_t c = 0; c < cluster_count; ++c)
+			if (cluster_index_offsets[c + 1] < cluster_index_offsets[c] || cluster_index_offsets[c + 1] - cluster_index_offsets[c] > 768)
+				return fail(CLODB200_ERR_INVALID, "clodb200_localIndicesBatch: clusters hold at most 256 triangles");
+		ensure_workspace(index_count * 5 + cluster_count * (vertex_capacity * 4 + 16) + (16 << 20), 16 << 20);
+		u32* dind = g_ws.persist.alloc<u32>(index_count);
+		u64* doff = g_ws.persist.alloc<u64>(cluster_count + 1);
+		u32* dvert = g_ws.persist.alloc<u32>(cluster_count * vertex_capacity);
+		u8* dtri = g_ws.persist.alloc<u8>(index_count);
+		u32* dcount = g_ws.persist.alloc<u32>(cluster_count);
+		dev_h2d(dind, indices, index_count * 4);
+		dev_h2d(doff, cluster_index_offsets, (cluster_count + 1) * 8);
+		dev_memset(dvert, 0, cluster_count * vertex_capacity * 4);
+		local_indices(dind, doff, u32(cluster_count), u32(vertex_capacity), dvert, dtri, dcount);
+		dev_d2h(out_vertices, dvert, cluster_count * vertex_capacity * 4);
+		dev_d2h(out_triangles, dtri, index_count);
+		dev_d2h(out_vertex_counts, dcount, cluster_count * 4);
+		return CLODB200_OK;
+	});
+}
+
+size_t clodb200_localIndices(unsigned int* vertices, unsigned char* triangles, const unsigned int* indices, size_t index_count)
+{
+	if (index_count == 0)
+		return 0;
+	uint64_t offsets[2] = {0, index_count};
+	unsigned int tmp[256];
+	unsigned int count = 0;
+	if (clodb200_localIndicesBatch(indices, offsets, 1, 256, tmp, triangles, &count) != CLODB200_OK)
+		return 0;
+	memcpy(vertices, tmp, size_t(count) * sizeof(unsigned int));
+	return count;
+}
+
 int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* indices, const unsigned int* group_index_offsets, size_t group_count,
     const float* positions, size_t vertex_count, size_t positions_stride,
     const float* attributes, size_t attributes_stride, const float* attribute_weights, size_t attribute_count,

@@ -97,6 +97,10 @@ void gather_group_triangles(const u32* tri, const u32* cluster_tri_offset, const
 // clod::lockBoundary (clusterlod.h:512-559): bit0 = position class touched by >= 2 groups, keeps bit1 (protect), ORs vertex_lock
 void lock_boundary(const u32* gtri, const u32* tri_group_offsets_dev, u32 group_count, u32 triangle_count, const u32* remap, const u8* vertex_lock, size_t vertex_count, u8* locks, Arena& temp);
 
+// ---- S8: group output (output.cu) -----------------------------------------------------------------------------------
+// clodLocalIndices (clusterlod.h:972-1023) for a batch of clusters; vertices holds vertex_capacity slots per cluster
+void local_indices(const u32* indices, const u64* cluster_index_offset, u32 cluster_count, u32 vertex_capacity, u32* vertices, u8* triangles, u32* vertex_count);
+
 // ---- S6: simplification (simplify.cu) -------------------------------------------------------------------------------
 struct SimplifyOutput
 {

@@ -421,9 +421,11 @@ DEVFN ScanElem load_elem(const Box* boxes, const u32* order, const u32* node_of_
 	u32 p = backward ? T - 1 - j : j;
 	u32 n = node_of_pos[p];
 	ScanElem e;
-	const Box& b = boxes[order[p]];
-	e.mn[0] = b.min[0], e.mn[1] = b.min[1], e.mn[2] = b.min[2];
-	e.mx[0] = b.max[0], e.mx[1] = b.max[1], e.mx[2] = b.max[2];
+	// the 32-byte box is gathered with two 16-byte loads (one sector) instead of six scalar ones
+	const float4* bp = reinterpret_cast<const float4*>(boxes + order[p]);
+	float4 lo = __ldg(bp), hi = __ldg(bp + 1);
+	e.mn[0] = lo.x, e.mn[1] = lo.y, e.mn[2] = lo.z;
+	e.mx[0] = hi.x, e.mx[1] = hi.y, e.mx[2] = hi.z;
 	e.flag = n == NODE_DONE || (backward ? p == node_begin[n] + node_count[n] - 1 : p == node_begin[n]);
 	return e;
 }

@@ -36,8 +36,7 @@ PROTECT_MASK = 7
 # what the kernel must read and write once if every operand moved exactly once.
 KERNEL_BYTES_PER_THREAD = {
     # segmented SAH area scan, 4 elements per thread: order u32 + gathered box 32 B + node id u32 (+ area f32 out)
-    "k_sa_apply": 4 * (4 + 32 + 4 + 4),
-    "k_sa_reduce": 4 * (4 + 32 + 4),
+    "k_sa_chained": 4 * (4 + 32 + 4 + 4),
     # radix sort scatter, 8 keys per thread: key in + key out + value in + value out (u32 keys)
     "(k_rs_scatter<K>)": 8 * 16,
     "k_rs_scatter<K>": 8 * 16,
@@ -53,8 +52,8 @@ KERNEL_BYTES_PER_THREAD = {
     "k_rank": 9 + 2 * (44 + 12) + 4 + 8,
     "k_build_clusters": 128 * 3 * 4 * 2 + 4 * 4,
     "k_cluster_bounds": 128 * 3 * 16 + 16,
-    "(k_scan_apply<T, Op>)": 8 * 8,
-    "(k_scan_reduce<T, Op>)": 8 * 4,
+    # chained single-pass scan, 8 u32 elements per thread, read once + written once
+    "(k_scan_chained<T, Op>)": 8 * 8,
 }
 
 
@@ -119,7 +118,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    from basicrenderer_b200 import load
+    from basicrenderer_b200 import load, sharding
 
     lib = load(local)
     mesh = _workload(rank, world)
@@ -146,6 +145,10 @@ def run_ours(args):
     lib.timer_start()
     for _ in range(args.steps):
         rec = lib.build_dag_resident(handle, keep_indices=False)
+        if world > 1:
+            # the path's only exchange: per-mesh metadata to every rank (NCCL all-gather of sizes + padded blobs)
+            gathered = sharding.gather_metadata([rank], [sharding.dag_summary_blob(rec)])
+            assert len(gathered) == world
     ms = lib.timer_stop_ms()
     launches = lib.launch_count - launches0
     barrier()

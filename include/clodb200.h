@@ -12,6 +12,9 @@
  *                                      meshopt_optimizeMeshlet), batched over independent index segments
  *   clodb200_computeClusterBounds   <- meshopt_computeClusterBounds via clod::boundsCompute, clusterlod.h:270-281
  *   clodb200_build / clodb200_buildEx <- clodBuild / clodBuildEx, clusterlod.h:159-184 (same structs, same callback)
+ *   clodb200_localIndices           <- clodLocalIndices, clusterlod.h:184 (implementation :972-1023)
+ *   clodb200_lockBoundary           <- clod::lockBoundary, clusterlod.h:512-559
+ *   clodb200_simplifyGroups         <- clod::simplify, clusterlod.h:601-659 (meshopt_simplifyWithAttributes per group)
  */
 #ifndef CLODB200_H
 #define CLODB200_H
@@ -81,6 +84,15 @@ int clodb200_clusterize(const clodb200_config* config, const unsigned int* indic
 /* Bounding sphere {cx, cy, cz, r} per cluster; clusters are given as cluster-major indices + per-cluster index counts. */
 int clodb200_computeClusterBounds(const unsigned int* indices, const unsigned int* cluster_index_counts, size_t cluster_count,
     const float* positions, size_t vertex_count, size_t positions_stride, float* out_bounds4);
+
+/* clodLocalIndices (clusterlod.h:972-1023): vertices[] = distinct indices in first-occurrence order, triangles[i] = position
+ * of indices[i] in vertices[]; returns the number of unique vertices (0 on failure). index_count <= 768, at most 256
+ * distinct vertices, exactly as the reference's unsigned char triangle ids imply. */
+size_t clodb200_localIndices(unsigned int* vertices, unsigned char* triangles, const unsigned int* indices, size_t index_count);
+/* The same for many clusters in one call: cluster c owns indices [cluster_index_offsets[c], cluster_index_offsets[c+1]);
+ * out_vertices holds vertex_capacity slots per cluster, out_triangles one byte per index, out_vertex_counts one per cluster. */
+int clodb200_localIndicesBatch(const unsigned int* indices, const uint64_t* cluster_index_offsets, size_t cluster_count, size_t vertex_capacity,
+    unsigned int* out_vertices, unsigned char* out_triangles, unsigned int* out_vertex_counts);
 
 /* clod::lockBoundary (clusterlod.h:512-559) for one DAG level. indices holds the merged index lists of all groups back
  * to back, group_index_offsets[group_count + 1] delimits them. locks[vertex_count] is updated in place: bit0 = position

@@ -219,3 +219,15 @@ def simplify(positions, indices, locks, target_count, attributes=None, attribute
     err = C.c_float(0)
     n = lib().clodref_simplify(C.byref(cfg), _ptr(indices), indices.size, _ptr(positions), positions.shape[0], 12, _ptr(attributes), astride, _ptr(attribute_weights), acount, _ptr(locks), target_count, _ptr(out), C.byref(err))
     return out[:n].copy(), err.value
+
+
+def local_indices(indices: np.ndarray):
+    """The reference's clodLocalIndices (clusterlod.h:972-1023) -> (vertices[unique], triangles u8)"""
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    vertices = np.zeros(max(1, indices.size), dtype=np.uint32)
+    triangles = np.zeros(indices.size, dtype=np.uint8)
+    fn = lib().clodLocalIndices
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    n = fn(_ptr(vertices), _ptr(triangles), _ptr(indices), indices.size)
+    return vertices[:n].copy(), triangles
