@@ -341,6 +341,63 @@ KERNEL k_relabel_clusters(u32* label, const u32* __restrict__ parent, u32 K)
 	label[c] = parent[label[c]];
 }
 
+// ---- group-graph contraction by hashing (one merge round) ------------------------------------------------------------
+// Relabels every edge to the merged groups, drops self loops and combines parallel edges by inserting (src, dst) into an
+// open-addressed table that accumulates the shared-vertex weight. The first inserter of a key also counts the edge for
+// the CSR of its source. Rows of the rebuilt CSR are unordered; every consumer (k_pick_neighbor, k_merge_pairs) is
+// order independent, so the result is deterministic.
+DEVFN u32 hash_edge(u64 key)
+{
+	key ^= key >> 33;
+	key *= 0xff51afd7ed558ccdull;
+	key ^= key >> 33;
+	key *= 0xc4ceb9fe1a85ec53ull;
+	key ^= key >> 33;
+	return u32(key);
+}
+
+KERNEL k_contract_insert(const u32* __restrict__ src, const u32* __restrict__ dst, const u32* __restrict__ w, const u32* __restrict__ parent, const u32* __restrict__ edge_count, u64 K, u64* table_key, u32* table_w, u32 mask,
+    u32* row_count, u32* new_edge_count)
+{
+	size_t e = GTID;
+	if (e >= *edge_count)
+		return;
+	u64 s = parent[src[e]], d = parent[dst[e]];
+	if (s == d)
+		return;
+	u64 key = s * K + d;
+	u32 slot = hash_edge(key) & mask;
+	for (;;)
+	{
+		u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&table_key[slot]), ~0ull, (unsigned long long)key);
+		if (old == ~0ull)
+		{
+			atomicAdd(&row_count[s], 1u);
+			atomicAdd(new_edge_count, 1u);
+			break;
+		}
+		if (old == key)
+			break;
+		slot = (slot + 1) & mask;
+	}
+	atomicAdd(&table_w[slot], w[e]);
+}
+
+KERNEL k_contract_fill(const u64* __restrict__ table_key, const u32* __restrict__ table_w, u32 table_size, u64 K, const u32* __restrict__ row_offset, u32* row_cursor, u32* src_out, u32* dst_out, u32* w_out)
+{
+	size_t slot = GTID;
+	if (slot >= table_size)
+		return;
+	u64 key = table_key[slot];
+	if (key == ~0ull)
+		return;
+	u32 s = u32(key / K), d = u32(key % K);
+	u32 pos = row_offset[s] + atomicAdd(&row_cursor[s], 1u);
+	src_out[pos] = s;
+	dst_out[pos] = d;
+	w_out[pos] = table_w[slot];
+}
+
 KERNEL k_relabel_edges(const u32* __restrict__ src, const u32* __restrict__ dst, const u32* __restrict__ parent, u32 E, u64 K, u64* edge_key, u32* keep)
 {
 	size_t e = GTID;
@@ -762,38 +819,56 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 	rebuild_offsets();
 
 	// ---- merge rounds
+	// scalars: [1] merges this round, [3] smallest open size, [8] current edge count, [9] next edge count
 	u32 rounds = 0;
-	while (E > 0)
+	if (E > 0)
 	{
-		rounds++;
-		dev_memset(scalars + 3, 0xff, sizeof(u32));
-		LAUNCH(k_pick_neighbor, K, info, e_off, e_dst, e_w, K, target, max_size, config.partition_spatial ? 1 : 0, best, best_score, scalars + 3);
-		iota(parent, K);
-		dev_memset(scalars + 1, 0, sizeof(u32));
-		dev_memset(claim, 0, size_t(K) * sizeof(u64));
-		LAUNCH(k_propose, K, info, best, best_score, K, scalars + 3, claim);
-		LAUNCH(k_merge_pairs, K, info, best, e_off, e_dst, e_w, K, scalars + 3, claim, parent, scalars + 1);
-		u32 merged = dev_read(scalars + 1);
-		if (merged == 0)
-			break;
-		LAUNCH(k_relabel_clusters, K, label, parent, K);
-		// contract the group graph
-		u32* keep = e_flag;
-		LAUNCH(k_relabel_edges, E, e_src, e_dst, parent, E, u64(K), e_key, keep);
-		exclusive_scan_u32(keep, keep, E, scalars, temp);
-		u32 E1 = dev_read(scalars);
-		LAUNCH(k_compact_edges, E, e_key, e_w, keep, E1, E, e_key_tmp, e_val_tmp);
-		std::swap(e_key, e_key_tmp);
-		std::swap(e_val, e_val_tmp); // e_val now holds the compacted weights
-		radix_sort_pairs<u64>(e_key, e_key_tmp, e_val, e_val_tmp, E1, 0, key_bits, temp);
-		LAUNCH(k_edge_run_heads, E1, e_key, e_val, E1, e_flag);
-		exclusive_scan_u32(e_flag, e_flag, E1, scalars, temp);
-		u32 E2 = dev_read(scalars);
-		LAUNCH(k_edge_combine, E1, e_key, e_val, e_flag, E2, E1, u64(K), e_src, e_dst, e_w);
-		E = E2;
-		rebuild_offsets();
-		if (rounds > 4096)
-			break;
+		size_t table_cap = 1;
+		while (table_cap < size_t(E) * 2)
+			table_cap <<= 1;
+		u64* table_key = temp.alloc<u64>(table_cap);
+		u32* table_w = temp.alloc<u32>(table_cap);
+		u32* e_src_alt = temp.alloc<u32>(E);
+		u32* e_dst_alt = temp.alloc<u32>(E);
+		u32* e_w_alt = temp.alloc<u32>(E);
+		u32* row_cursor = temp.alloc<u32>(K);
+		dev_h2d(scalars + 8, &E, sizeof(u32));
+		u32 E_cur = E;
+		for (;;)
+		{
+			rounds++;
+			dev_memset(scalars + 3, 0xff, sizeof(u32));
+			LAUNCH(k_pick_neighbor, K, info, e_off, e_dst, e_w, K, target, max_size, config.partition_spatial ? 1 : 0, best, best_score, scalars + 3);
+			iota(parent, K);
+			dev_memset(scalars + 1, 0, sizeof(u32));
+			dev_memset(claim, 0, size_t(K) * sizeof(u64));
+			LAUNCH(k_propose, K, info, best, best_score, K, scalars + 3, claim);
+			LAUNCH(k_merge_pairs, K, info, best, e_off, e_dst, e_w, K, scalars + 3, claim, parent, scalars + 1);
+			u32 merged = dev_read(scalars + 1);
+			if (merged == 0 || rounds > 4096)
+				break;
+			LAUNCH(k_relabel_clusters, K, label, parent, K);
+			// contract the group graph
+			size_t cap = 1;
+			while (cap < size_t(E_cur) * 2)
+				cap <<= 1;
+			dev_memset(table_key, 0xff, cap * sizeof(u64));
+			dev_memset(table_w, 0, cap * sizeof(u32));
+			dev_memset(e_off, 0, (size_t(K) + 1) * sizeof(u32));
+			dev_memset(row_cursor, 0, size_t(K) * sizeof(u32));
+			dev_memset(scalars + 9, 0, sizeof(u32));
+			LAUNCH(k_contract_insert, E_cur, e_src, e_dst, e_w, parent, scalars + 8, u64(K), table_key, table_w, u32(cap - 1), e_off, scalars + 9);
+			exclusive_scan_u32(e_off, e_off, size_t(K) + 1, nullptr, temp);
+			LAUNCH(k_contract_fill, cap, table_key, table_w, u32(cap), u64(K), e_off, row_cursor, e_src_alt, e_dst_alt, e_w_alt);
+			dev_d2d(scalars + 8, scalars + 9, sizeof(u32));
+			std::swap(e_src, e_src_alt);
+			std::swap(e_dst, e_dst_alt);
+			std::swap(e_w, e_w_alt);
+			// every merge removes at least the two directed edges between the merged pair
+			E_cur = E_cur > 2 * merged ? E_cur - 2 * merged : 0;
+			if (E_cur == 0)
+				break;
+		}
 	}
 
 	// ---- leftovers: spatially merge open groups (only when positions are used, partition.cpp:599-611)
