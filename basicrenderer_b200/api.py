@@ -260,21 +260,28 @@ class ClodLib:
             keep.append(vertex_lock)
         return d, keep
 
-    def _record(self, handle) -> DagRecord:
+    def _record(self, handle, views: bool = False) -> DagRecord:
+        """views=True returns zero-copy views into the library's (recycled) record buffers: valid only until the next
+        build call on this process (what a C caller of the callback ABI sees); the default copies."""
         if not handle:
             raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200 build failed")
         arrays = {}
         for name, dtype in _RECORD_DTYPES.items():
             ptr, size = C.c_void_p(), C.c_size_t()
             self._lib.clodb200_recordGet(handle, name.encode(), C.byref(ptr), C.byref(size))
-            arrays[name] = np.frombuffer((C.c_ubyte * size.value).from_address(ptr.value), dtype=dtype).copy() if size.value else np.zeros(0, dtype)
+            if not size.value:
+                arrays[name] = np.zeros(0, dtype)
+                continue
+            view = np.frombuffer((C.c_ubyte * size.value).from_address(ptr.value), dtype=dtype)
+            arrays[name] = view if views else view.copy()
         self._lib.clodb200_recordFree(handle)
         return DagRecord(arrays)
 
     def build_dag(self, positions, indices, attributes=None, attribute_weights=None, protect_mask=0, config: Config | None = None, **kw) -> DagRecord:
         """clodBuildEx-equivalent on host arrays (upload + build + read-back), recording the callback stream."""
+        views = bool(kw.pop("views", False))
         desc, keep = self.mesh_desc(positions, indices, attributes, attribute_weights, protect_mask, **kw)
-        return self._record(self._lib.clodb200_buildRecorded(config or self.builder_config(), desc))
+        return self._record(self._lib.clodb200_buildRecorded(config or self.builder_config(), desc), views=views)
 
     def upload_mesh(self, positions, indices, attributes=None, attribute_weights=None, protect_mask=0, **kw):
         desc, keep = self.mesh_desc(positions, indices, attributes, attribute_weights, protect_mask, **kw)

@@ -478,6 +478,53 @@ int clodb200_simplifyGroups(const clodb200_config* config, const unsigned int* i
 	});
 }
 
+// Small cache of device blocks for mesh uploads: cudaMalloc / cudaFree per call cost milliseconds and cudaFree synchronises the
+// device. Freed blocks are kept (up to 8) and handed out again to requests they can hold without wasting more than 2x.
+struct DeviceBlock
+{
+	void* ptr;
+	size_t bytes;
+};
+static std::vector<DeviceBlock> g_block_cache;
+
+static void* block_alloc(size_t bytes, std::vector<DeviceBlock>& owned)
+{
+	bytes = bytes ? bytes : 1;
+	size_t best = g_block_cache.size();
+	for (size_t i = 0; i < g_block_cache.size(); ++i)
+		if (g_block_cache[i].bytes >= bytes && g_block_cache[i].bytes <= bytes * 2 + 4096 && (best == g_block_cache.size() || g_block_cache[i].bytes < g_block_cache[best].bytes))
+			best = i;
+	DeviceBlock b;
+	if (best != g_block_cache.size())
+	{
+		b = g_block_cache[best];
+		g_block_cache.erase(g_block_cache.begin() + best);
+	}
+	else
+	{
+		b.ptr = dev_malloc(bytes);
+		b.bytes = bytes;
+	}
+	owned.push_back(b);
+	return b.ptr;
+}
+
+static void block_release(std::vector<DeviceBlock>& owned)
+{
+	for (const DeviceBlock& b : owned)
+		g_block_cache.push_back(b);
+	owned.clear();
+	while (g_block_cache.size() > 8)
+	{
+		size_t smallest = 0;
+		for (size_t i = 1; i < g_block_cache.size(); ++i)
+			if (g_block_cache[i].bytes < g_block_cache[smallest].bytes)
+				smallest = i;
+		dev_free(g_block_cache[smallest].ptr);
+		g_block_cache.erase(g_block_cache.begin() + smallest);
+	}
+}
+
 KERNEL k_index_range(const u32* __restrict__ indices, size_t n, u32 vertex_count, u32* bad)
 {
 	size_t i = GTID;
@@ -490,7 +537,7 @@ struct clodb200_device_mesh
 	DeviceMesh mesh;
 	u32* indices = nullptr;
 	size_t index_count = 0;
-	std::vector<void*> allocations;
+	std::vector<DeviceBlock> allocations;
 };
 
 static bool validate_mesh(const clodb200_mesh& mesh)
@@ -521,8 +568,7 @@ static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
 	try
 	{
 		size_t V = mesh.vertex_count;
-		float* dpos = static_cast<float*>(dev_malloc(V * 12));
-		dm->allocations.push_back(dpos);
+		float* dpos = static_cast<float*>(block_alloc(V * 12, dm->allocations));
 		if (mesh.vertex_positions_stride == 12)
 			dev_h2d(dpos, mesh.vertex_positions, V * 12);
 		else
@@ -539,8 +585,7 @@ static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
 		size_t astride = mesh.vertex_attributes_stride / 4;
 		if (mesh.vertex_attributes && astride)
 		{
-			float* dattr = static_cast<float*>(dev_malloc(V * astride * 4));
-			dm->allocations.push_back(dattr);
+			float* dattr = static_cast<float*>(block_alloc(V * astride * 4, dm->allocations));
 			dev_h2d(dattr, mesh.vertex_attributes, V * astride * 4);
 			dm->mesh.attributes = dattr;
 			dm->mesh.attribute_stride = u32(astride);
@@ -551,18 +596,15 @@ static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
 		}
 		if (mesh.vertex_lock)
 		{
-			u8* dl = static_cast<u8*>(dev_malloc(V));
-			dm->allocations.push_back(dl);
+			u8* dl = static_cast<u8*>(block_alloc(V, dm->allocations));
 			dev_h2d(dl, mesh.vertex_lock, V);
 			dm->mesh.vertex_lock = dl;
 		}
-		dm->indices = static_cast<u32*>(dev_malloc(mesh.index_count * 4));
-		dm->allocations.push_back(dm->indices);
+		dm->indices = static_cast<u32*>(block_alloc(mesh.index_count * 4, dm->allocations));
 		dev_h2d(dm->indices, mesh.indices, mesh.index_count * 4);
 		dm->index_count = mesh.index_count;
 		// range check on the device copy (the reference asserts; a bad index would read out of bounds in every stage)
-		u32* bad = static_cast<u32*>(dev_malloc(sizeof(u32)));
-		dm->allocations.push_back(bad);
+		u32* bad = static_cast<u32*>(block_alloc(sizeof(u32), dm->allocations));
 		dev_memset(bad, 0, sizeof(u32));
 		LAUNCH(k_index_range, mesh.index_count, dm->indices, mesh.index_count, u32(V), bad);
 		if (dev_read(bad))
@@ -570,8 +612,7 @@ static clodb200_device_mesh* upload_mesh_locked(const clodb200_mesh& mesh)
 	}
 	catch (...)
 	{
-		for (void* p : dm->allocations)
-			dev_free(p);
+		block_release(dm->allocations);
 		delete dm;
 		throw;
 	}
@@ -582,8 +623,7 @@ static void free_mesh_locked(clodb200_device_mesh* dm)
 {
 	if (!dm)
 		return;
-	for (void* p : dm->allocations)
-		dev_free(p);
+	block_release(dm->allocations);
 	delete dm;
 }
 
@@ -695,9 +735,12 @@ size_t clodb200_buildEx(clodb200_config config, clodb200_mesh mesh, void* output
 	return build_host(config, mesh, output_context, output_callback, nullptr);
 }
 
+static clodb200_record* g_record_pool = nullptr; // one recycled record (buffers keep their capacity between builds)
+
 static clodb200_record* record_build(const clodb200_config& config, const clodb200_device_mesh* dm, bool keep_indices)
 {
-	clodb200_record* rec = new clodb200_record();
+	clodb200_record* rec = g_record_pool ? g_record_pool : new clodb200_record();
+	g_record_pool = nullptr;
 	try
 	{
 		RecordSink sink;
@@ -774,7 +817,17 @@ int clodb200_recordGet(const clodb200_record* record, const char* name, const vo
 
 void clodb200_recordFree(clodb200_record* record)
 {
-	delete record;
+	if (!record)
+		return;
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (!g_record_pool)
+	{
+		for (auto& kv : record->blobs)
+			kv.second.clear(); // keeps the capacity
+		g_record_pool = record;
+	}
+	else
+		delete record;
 }
 
 #ifndef CLODB_EMU

@@ -885,6 +885,171 @@ KERNEL k_build_clusters(const u32* __restrict__ cluster_tri_offset, u32 K, const
 	cluster_segment[c] = seg_of_tri[order0[begin]];
 }
 
+#ifndef CLODB_EMU
+// Warp-cooperative version of k_build_clusters (same results): one warp per cluster, all tables in shared memory.
+//   * local vertex ids in first-occurrence order: every corner inserts its vertex into a shared hash table that keeps the
+//     lowest corner index per vertex; a vertex's id is the number of "first" corners before its own first corner;
+//   * meshopt_optimizeMeshlet: the serial "next triangle" search becomes ballots over the still-unplaced triangles (each
+//     lane owns triangles lane, lane + 32, ...), so "first triangle in remaining order with >= 2 cached vertices, else
+//     first with 1, else first" is a find-first-set; the reference's memmove only preserves that remaining order.
+static const int BC_WARPS = 4;
+static __global__ void __launch_bounds__(BC_WARPS * 32) k_build_clusters_warp(const u32* __restrict__ cluster_tri_offset, u32 K, const u32* __restrict__ order0, const u32* __restrict__ tri, const u32* __restrict__ seg_of_tri,
+    u32* tri_out, u32* cluster_vertex_count, u32* cluster_segment, int optimize)
+{
+	__shared__ u32 s_keys[BC_WARPS][512];
+	__shared__ u32 s_min[BC_WARPS][512]; // lowest corner index per table slot, later the vertex's local id
+	__shared__ u32 s_verts[BC_WARPS][128];
+	__shared__ u8 s_idx[BC_WARPS][384];
+	__shared__ u8 s_out[BC_WARPS][384];
+	__shared__ u8 s_cache[BC_WARPS][128];
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 c = blockIdx.x * BC_WARPS + warp;
+	if (c >= K)
+		return;
+	u32* keys = s_keys[warp];
+	u32* vmin = s_min[warp];
+	u32* verts = s_verts[warp];
+	u8* idx = s_idx[warp];
+	u8* out = s_out[warp];
+	u8* cache = s_cache[warp];
+
+	const u32 begin = cluster_tri_offset[c], count = cluster_tri_offset[c + 1] - begin;
+	const u32 corners = count * 3;
+	for (int i = lane; i < 512; i += 32)
+	{
+		keys[i] = 0xffffffffu;
+		vmin[i] = 0xffffffffu;
+	}
+	__syncwarp();
+
+	// ---- corners -> table slots (12 corners per lane at most)
+	u32 cv[12];
+	u32 cslot[12];
+#pragma unroll
+	for (int r = 0; r < 12; ++r)
+	{
+		u32 j = lane + 32 * r;
+		cv[r] = 0;
+		cslot[r] = 0;
+		if (j < corners)
+		{
+			u32 t = order0[begin + j / 3];
+			u32 v = tri[size_t(t) * 3 + j % 3];
+			u32 h = (v * 0x9E3779B1u) >> 23;
+			for (;;)
+			{
+				u32 old = atomicCAS(&keys[h], 0xffffffffu, v);
+				if (old == 0xffffffffu || old == v)
+					break;
+				h = (h + 1) & 511;
+			}
+			atomicMin(&vmin[h], j);
+			cv[r] = v;
+			cslot[r] = h;
+		}
+	}
+	__syncwarp();
+	// ---- rank the first occurrences in corner order
+	u32 vcount = 0;
+	bool first[12];
+	u32 rank[12];
+#pragma unroll
+	for (int r = 0; r < 12; ++r)
+	{
+		u32 j = lane + 32 * r;
+		first[r] = j < corners && vmin[cslot[r]] == j;
+		unsigned mask = __ballot_sync(0xffffffffu, first[r]);
+		rank[r] = vcount + __popc(mask & ((1u << lane) - 1));
+		vcount += __popc(mask);
+	}
+	__syncwarp();
+#pragma unroll
+	for (int r = 0; r < 12; ++r)
+		if (first[r])
+		{
+			vmin[cslot[r]] = rank[r]; // slot now holds the local id
+			verts[rank[r]] = cv[r];
+		}
+	__syncwarp();
+#pragma unroll
+	for (int r = 0; r < 12; ++r)
+	{
+		u32 j = lane + 32 * r;
+		if (j < corners)
+			idx[j] = u8(vmin[cslot[r]]);
+	}
+	for (int i = lane; i < 128; i += 32)
+		cache[i] = 0;
+	__syncwarp();
+
+	const u8* final_idx = idx;
+	if (optimize)
+	{
+		// meshopt_optimizeMeshlet (clusterizer.cpp:1682-1770)
+		unsigned alive = 0; // bit s: triangle lane + 32 * s not placed yet
+#pragma unroll
+		for (int s4 = 0; s4 < 4; ++s4)
+			if (u32(lane + 32 * s4) < count)
+				alive |= 1u << s4;
+		u8 cache_last = 128;
+		for (u32 i = 0; i < count; ++i)
+		{
+			int match[4];
+#pragma unroll
+			for (int s4 = 0; s4 < 4; ++s4)
+			{
+				match[s4] = -1;
+				if (alive & (1u << s4))
+				{
+					u32 t = lane + 32 * s4;
+					int aok = u8(cache_last - cache[idx[t * 3 + 0]]) < 3;
+					int bok = u8(cache_last - cache[idx[t * 3 + 1]]) < 3;
+					int cok = u8(cache_last - cache[idx[t * 3 + 2]]) < 3;
+					match[s4] = aok + bok + cok;
+				}
+			}
+			int next = -1;
+#pragma unroll
+			for (int want = 2; want >= 0 && next < 0; --want)
+			{
+#pragma unroll
+				for (int s4 = 0; s4 < 4; ++s4)
+				{
+					unsigned m = __ballot_sync(0xffffffffu, want == 2 ? match[s4] >= 2 : match[s4] == want);
+					if (m && next < 0)
+						next = s4 * 32 + (__ffs(m) - 1);
+				}
+			}
+			u8 a = idx[next * 3 + 0], b = idx[next * 3 + 1], cc = idx[next * 3 + 2];
+			if ((next & 31) == lane)
+				alive &= ~(1u << (next >> 5));
+			cache_last++;
+			__syncwarp();
+			if (lane == 0)
+			{
+				out[i * 3 + 0] = a;
+				out[i * 3 + 1] = b;
+				out[i * 3 + 2] = cc;
+				cache[a] = cache_last;
+				cache[b] = cache_last;
+				cache[cc] = cache_last;
+			}
+			__syncwarp();
+		}
+		final_idx = out;
+	}
+
+	for (u32 j = lane; j < corners; j += 32)
+		tri_out[size_t(begin) * 3 + j] = verts[final_idx[j]];
+	if (lane == 0)
+	{
+		cluster_vertex_count[c] = vcount;
+		cluster_segment[c] = seg_of_tri[order0[begin]];
+	}
+}
+#endif
+
 KERNEL k_gather_u32(const u32* __restrict__ src, const u32* __restrict__ index, u32* dst, u32 n)
 {
 	size_t i = GTID;
@@ -1064,7 +1229,11 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 	result.cluster_segment = ws.persist.alloc<u32>(K);
 
 	LAUNCH(k_cluster_starts, size_t(T) + 1, boundary, rank, result.cluster_tri_offset, T, K);
+#ifdef CLODB_EMU
 	LAUNCH(k_build_clusters, K, result.cluster_tri_offset, K, order[0], tri, seg_of_tri, result.tri, result.cluster_vertex_count, result.cluster_segment, config.optimize_clusters ? 1 : 0);
+#else
+	LAUNCH_GRID(k_build_clusters_warp, (K + BC_WARPS - 1) / BC_WARPS, BC_WARPS * 32, result.cluster_tri_offset, K, order[0], tri, seg_of_tri, result.tri, result.cluster_vertex_count, result.cluster_segment, config.optimize_clusters ? 1 : 0);
+#endif
 	return result;
 }
 

@@ -157,11 +157,11 @@ def run_ours(args):
 
     # ---- end to end through the host-pointer C ABI (upload + build + read-back every step)
     for _ in range(min(args.warmup, 2)):
-        lib.build_dag(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK)
+        lib.build_dag(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK, views=True)
     barrier()
     lib.timer_start()
     for _ in range(args.steps):
-        rec_e2e = lib.build_dag(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK)
+        rec_e2e = lib.build_dag(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK, views=True)
     ms_e2e = lib.timer_stop_ms()
     barrier()
     h2d = positions.nbytes + normals.nbytes + indices.nbytes
