@@ -6,6 +6,8 @@ All generators are pure numpy, seeded, and produce byte-identical output on ever
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 VERTEX_NORMALS = 1 << 0  # BasicRenderer/include/Mesh/VertexFlags.h
@@ -97,12 +99,25 @@ def grid(n: int, seed: int = 1234, amplitude: float = 0.1, chunk: int = 1 << 22)
     nx = np.empty_like(px)
     ny = np.empty_like(px)
     eps = 0.5 / n
-    for s in range(0, px.size, chunk):
+
+    def work(s):
         e = min(px.size, s + chunk)
         x, y = px[s:e], py[s:e]
         pz[s:e] = height(x, y)
         nx[s:e] = (height(x + eps, y) - height(x - eps, y)) / (2 * eps)
         ny[s:e] = (height(x, y + eps) - height(x, y - eps)) / (2 * eps)
+
+    # chunks are independent and numpy releases the GIL inside its loops: generate them on all host cores
+    chunk = min(chunk, 1 << 18)
+    starts = list(range(0, px.size, chunk))
+    if len(starts) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            list(ex.map(work, starts))
+    else:
+        for s in starts:
+            work(s)
     nrm = np.stack([-nx, -ny, np.ones_like(nx)], axis=1)
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     verts = np.concatenate([np.stack([px, py, pz], axis=1), nrm], axis=1).astype(np.float32)
