@@ -41,8 +41,10 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build_product(force: bool = False, verbose: bool = False) -> str:
-    objdir = os.path.join(ROOT, "build", "product")
+def build_product(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: str | None = None, tag: str = "product") -> str:
+    """extra_flags / lib_path / tag build tuning variants next to the product library (tools/tune_*.py)."""
+    objdir = os.path.join(ROOT, "build", tag)
+    target_lib = lib_path or PRODUCT_LIB
     os.makedirs(objdir, exist_ok=True)
     hdrs = _headers()
     jobs = []
@@ -55,14 +57,14 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
             # -fmad=false: the reference is IEEE x86-64 code without FMA contraction; keeping mul/add separate is what
             # makes the float stages reproduce its results bit for bit
             jobs.append([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-                         "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-c", s, "-o", o])
+                         "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3"] + list(extra_flags) + ["-c", s, "-o", o])
     with ThreadPoolExecutor(max_workers=8) as ex:
         outs = list(ex.map(_run, jobs))
     if verbose:
         print("\n".join(outs))
-    if jobs or force or not os.path.exists(PRODUCT_LIB):
-        _run([NVCC, "-shared", "-o", PRODUCT_LIB] + objs + ["-lcudart"])
-    return PRODUCT_LIB
+    if jobs or force or not os.path.exists(target_lib):
+        _run([NVCC, "-shared", "-o", target_lib] + objs + ["-lcudart"])
+    return target_lib
 
 
 def build_emu(force: bool = False) -> str:

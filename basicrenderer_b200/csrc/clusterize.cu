@@ -210,10 +210,14 @@ DEVFN void pack_tail(u8* boundary, const u32* order, const u32* tri, u32 begin, 
 // count <= max_triangles; the reference's recursion at this size touches <= 128 triangles per node).
 // Large nodes that hit the depth limit or found no admissible split are packed here as well.
 KERNEL k_resolve_nodes(const u32* __restrict__ node_begin, const u32* __restrict__ node_count, u64* node_best, u32* node_split, u32 node_total, int depth,
-    const u32* __restrict__ order0, const u32* __restrict__ order1, const u32* __restrict__ order2, const Box* __restrict__ boxes, const u32* __restrict__ tri, u8* boundary, SplitParams sp, int pass)
+    const u32* __restrict__ order0, const u32* __restrict__ order1, const u32* __restrict__ order2, const Box* __restrict__ boxes, const u32* __restrict__ tri, u8* boundary, SplitParams sp, int pass,
+    const u8* __restrict__ node_pending)
 {
 	size_t n = GTID;
 	if (n >= node_total)
+		return;
+	// pass 0 on the GPU: the warp-cooperative leaf test has already settled every node that fits the vertex limit
+	if (pass == 0 && node_pending && !node_pending[n])
 		return;
 	u32 begin = node_begin[n], count = node_count[n];
 	VertexSet set;
@@ -336,6 +340,67 @@ KERNEL k_resolve_nodes(const u32* __restrict__ node_begin, const u32* __restrict
 	node_best[n] = (u64(bestk) << 30) | u64(bestsplit - 1);
 }
 
+#ifndef CLODB_EMU
+// Leaf test of bvhSplit (clusterizer.cpp:1053-1054) for nodes within the triangle limit, one warp per node: the node's
+// corners are inserted into a shared-memory vertex set; nodes that also fit the vertex limit become meshlets here, the
+// (rare) vertex-bound ones are flagged for the serial k_resolve_nodes path.
+static const int LT_WARPS = 8;
+static __global__ void __launch_bounds__(LT_WARPS * 32) k_leaf_test_warp(const u32* __restrict__ node_begin, const u32* __restrict__ node_count, u64* node_best, u32* node_split, u32 node_total, const u32* __restrict__ order0,
+    const u32* __restrict__ tri, u8* boundary, SplitParams sp, u8* node_pending)
+{
+	__shared__ u32 s_keys[LT_WARPS][512];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 n = blockIdx.x * LT_WARPS + warp;
+	if (n >= node_total)
+		return;
+	const u32 begin = node_begin[n], count = node_count[n];
+	if (count > sp.max_triangles)
+	{
+		if (lane == 0)
+			node_pending[n] = 0;
+		return;
+	}
+	u32* keys = s_keys[warp];
+	for (int i = lane; i < 512; i += 32)
+		keys[i] = 0xffffffffu;
+	__syncwarp();
+	u32 fresh = 0;
+	for (u32 j = lane; j < count * 3; j += 32)
+	{
+		u32 t = order0[begin + j / 3];
+		u32 v = tri[size_t(t) * 3 + j % 3];
+		u32 h = (v * 0x9E3779B1u) >> 23;
+		for (;;)
+		{
+			u32 old = atomicCAS(&keys[h], 0xffffffffu, v);
+			if (old == 0xffffffffu)
+			{
+				fresh++;
+				break;
+			}
+			if (old == v)
+				break;
+			h = (h + 1) & 511;
+		}
+	}
+	for (int d = 16; d >= 1; d >>= 1)
+		fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
+	if (fresh <= sp.max_vertices)
+	{
+		for (u32 j = lane; j < count; j += 32)
+			boundary[begin + j] = j == 0 ? 1 : 0;
+		if (lane == 0)
+		{
+			node_split[n] = 0;
+			node_best[n] = ~u64(0);
+			node_pending[n] = 0;
+		}
+	}
+	else if (lane == 0)
+		node_pending[n] = 1;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // segmented prefix / suffix surface areas over active node ranges (bvhComputeArea, clusterizer.cpp:970-983)
 
@@ -410,8 +475,14 @@ DEVFN ScanElem scan_shfl_up(const ScanElem& e, int d)
 	return r;
 }
 
-static const int SA_THREADS = 256;
-static const int SA_ITEMS = 4;
+#ifndef CLODB_SA_THREADS
+#define CLODB_SA_THREADS 256
+#endif
+#ifndef CLODB_SA_ITEMS
+#define CLODB_SA_ITEMS 8
+#endif
+static const int SA_THREADS = CLODB_SA_THREADS;
+static const int SA_ITEMS = CLODB_SA_ITEMS;
 static const int SA_TILE = SA_THREADS * SA_ITEMS;
 
 DEVFN ScanElem load_elem(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, u32 T, u32 j, bool backward)
@@ -420,13 +491,20 @@ DEVFN ScanElem load_elem(const Box* boxes, const u32* order, const u32* node_of_
 		return scan_identity();
 	u32 p = backward ? T - 1 - j : j;
 	u32 n = node_of_pos[p];
+	if (n == NODE_DONE)
+	{
+		// finished nodes are never read by the pivot search: no box gather, and the scan restarts here
+		ScanElem done = scan_identity();
+		done.flag = 1;
+		return done;
+	}
 	ScanElem e;
 	// the 32-byte box is gathered with two 16-byte loads (one sector) instead of six scalar ones
 	const float4* bp = reinterpret_cast<const float4*>(boxes + order[p]);
 	float4 lo = __ldg(bp), hi = __ldg(bp + 1);
 	e.mn[0] = lo.x, e.mn[1] = lo.y, e.mn[2] = lo.z;
 	e.mx[0] = hi.x, e.mx[1] = hi.y, e.mx[2] = hi.z;
-	e.flag = n == NODE_DONE || (backward ? p == node_begin[n] + node_count[n] - 1 : p == node_begin[n]);
+	e.flag = backward ? p == node_begin[n] + node_count[n] - 1 : p == node_begin[n];
 	return e;
 }
 
@@ -471,6 +549,10 @@ struct OpSegBox
 	DEVFN ScanElem apply(const ScanElem& a, const ScanElem& b)
 	{
 		return scan_combine(a, b);
+	}
+	DEVFN bool prefix_independent(const ScanElem& a)
+	{
+		return a.flag != 0;
 	}
 };
 
@@ -1146,6 +1228,7 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 	u32* node_split = temp.alloc<u32>(node_cap);
 	u32* node_flags = temp.alloc<u32>(node_cap);
 	u32* node_total_dev = temp.alloc<u32>(4);
+	u8* node_pending = temp.alloc<u8>(node_cap);
 	u32* node_of_pos = temp.alloc<u32>(T);
 	u32* node_of_pos_alt = temp.alloc<u32>(T);
 	u8* boundary = temp.alloc<u8>(T);
@@ -1176,9 +1259,14 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 		{
 			seg_area_scan_all(boxes, order, node_of_pos, node_begin, node_count, areas, T, temp);
 			LAUNCH(k_pivot_large, size_t(T) * 3, node_of_pos, node_begin, node_count, areas, node_best, T, sp);
-			LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 1);
+			LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 1, nullptr);
 		}
-		LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 0);
+#ifdef CLODB_EMU
+		LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 0, nullptr);
+#else
+		LAUNCH_GRID(k_leaf_test_warp, (n_nodes + LT_WARPS - 1) / LT_WARPS, LT_WARPS * 32, node_begin, node_count, node_best, node_split, n_nodes, order[0], tri, boundary, sp, node_pending);
+		LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 0, node_pending);
+#endif
 
 		// children numbering
 		LAUNCH(k_split_flags, n_nodes, node_split, node_flags, n_nodes);

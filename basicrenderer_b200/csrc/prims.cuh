@@ -54,6 +54,10 @@ struct OpAddU32
 	{
 		return a + b;
 	}
+	HOSTDEVFN bool prefix_independent(u32)
+	{
+		return false;
+	}
 };
 
 struct OpMaxU64
@@ -65,6 +69,10 @@ struct OpMaxU64
 	HOSTDEVFN u64 apply(u64 a, u64 b)
 	{
 		return a > b ? a : b;
+	}
+	HOSTDEVFN bool prefix_independent(u64)
+	{
+		return false;
 	}
 };
 
@@ -257,11 +265,24 @@ DEVFN T scan_chain_lookback(u32 tile, const T& tile_aggregate, u32* flags, char*
 		}
 		return Op::identity();
 	}
+	// Segmented operators: when the tile contains a segment head, everything after the tile only depends on the tile itself,
+	// so its aggregate already is its inclusive prefix and can be published as such before looking back (successors then
+	// stop their look-back here instead of walking further).
+	const bool independent = Op::prefix_independent(tile_aggregate);
 	if (lane == 0)
 	{
-		st_value<T>(aggregate, tile, tile_aggregate);
-		__threadfence();
-		*reinterpret_cast<volatile u32*>(flags + tile) = tag_agg;
+		if (independent)
+		{
+			st_value<T>(inclusive, tile, tile_aggregate);
+			__threadfence();
+			*reinterpret_cast<volatile u32*>(flags + tile) = tag_inc;
+		}
+		else
+		{
+			st_value<T>(aggregate, tile, tile_aggregate);
+			__threadfence();
+			*reinterpret_cast<volatile u32*>(flags + tile) = tag_agg;
+		}
 	}
 	T prefix = Op::identity(); // combination of the predecessors visited so far (nearest block of them)
 	int p = int(tile) - 1;
@@ -296,7 +317,7 @@ DEVFN T scan_chain_lookback(u32 tile, const T& tile_aggregate, u32* flags, char*
 			break;
 		p -= 32;
 	}
-	if (lane == 0)
+	if (lane == 0 && !independent)
 	{
 		st_value<T>(inclusive, tile, Op::apply(prefix, tile_aggregate));
 		__threadfence();
