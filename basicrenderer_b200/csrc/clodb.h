@@ -116,6 +116,7 @@ struct SimplifyStats
 	u32 rounds = 0;
 	u32 max_rounds = 0;
 	u32 window_extensions = 0;
+	u32 sloppy_groups = 0;
 };
 extern SimplifyStats g_simplify_stats;
 // One meshopt_simplifyWithAttributes(Sparse|ErrorAbsolute|Permissive) per group, all groups batched. gtri holds each

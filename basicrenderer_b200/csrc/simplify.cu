@@ -1593,6 +1593,397 @@ KERNEL k_group_results(const GroupState* __restrict__ groups, const float* __res
 	out_error[g] = sqrtf(groups[g].result_error) * group_extent[g];
 }
 
+// =====================================================================================================================
+// Sloppy fallback: clod::simplifyFallback (clusterlod.h:567-599) -> meshopt_simplifySloppy (simplifier.cpp:2644-2774) on the
+// de-indexed group (one "vertex" per corner), + meshopt_simplifyScale (:2934-2944). Callees: rescalePositions :550-606,
+// computeVertexIds :2083-2101, countTriangles :2103-2117, fillVertexCells :2119-2143, fillCellQuadrics :2165-2193,
+// fillCellRemap :2233-2248, filterTriangles :2278-2321, interpolate :2323-2329.
+// It runs only for groups whose edge-collapse result misses the target (rare), one group at a time; every step is a
+// data-parallel kernel over the group's corners, with the reference's sequential semantics recovered by
+//   * lowest-corner-wins hash tables (cell numbering, duplicate-triangle filter) + order preserving compaction,
+//   * per-cell quadric sums taken over the cell's corners in ascending corner order (the serial accumulation order),
+//   * (error, corner) lexicographic argmin per cell.
+KERNEL k_sl_minmax(const u32* __restrict__ corner_vertex, const float* __restrict__ positions, u32 n, u32* mm)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	const float* p = positions + size_t(corner_vertex[i]) * 3;
+	for (int k = 0; k < 3; ++k)
+	{
+		atomicMin(&mm[k], float_order_key(p[k]));
+		atomicMax(&mm[3 + k], float_order_key(p[k]));
+	}
+}
+
+KERNEL k_sl_rescale(const u32* __restrict__ corner_vertex, const float* __restrict__ positions, u32 n, float minx, float miny, float minz, float scale, Vector3* vpos)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	const float* p = positions + size_t(corner_vertex[i]) * 3;
+	Vector3 r;
+	r.x = (p[0] - minx) * scale;
+	r.y = (p[1] - miny) * scale;
+	r.z = (p[2] - minz) * scale;
+	vpos[i] = r;
+}
+
+KERNEL k_sl_ids(const Vector3* __restrict__ vpos, const u32* __restrict__ corner_vertex, const u8* __restrict__ locks, u32 n, int grid_size, u32* ids)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	float cell_scale = float(grid_size - 1);
+	Vector3 v = vpos[i];
+	int xi = int(v.x * cell_scale + 0.5f);
+	int yi = int(v.y * cell_scale + 0.5f);
+	int zi = int(v.z * cell_scale + 0.5f);
+	if (locks && (locks[corner_vertex[i]] & 1))
+		ids[i] = (1u << 30) | u32(i);
+	else
+		ids[i] = (u32(xi) << 20) | (u32(yi) << 10) | u32(zi);
+}
+
+KERNEL k_sl_count_triangles(const u32* __restrict__ ids, u32 T, u32* count)
+{
+	size_t t = GTID;
+	if (t >= T)
+		return;
+	u32 a = ids[t * 3 + 0], b = ids[t * 3 + 1], c = ids[t * 3 + 2];
+	if ((a != b) & (a != c) & (b != c))
+		atomicAdd(count, 1u);
+}
+
+DEVFN u32 sl_hash(u32 h)
+{
+	h ^= h >> 13;
+	h *= 0x5bd1e995u;
+	h ^= h >> 15;
+	return h;
+}
+
+// cell table: lowest corner per distinct vertex id
+KERNEL k_sl_cell_insert(const u32* __restrict__ ids, u32 n, u32* table_id, u32* table_first, u32 mask, u32* slot_of)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	u32 id = ids[i];
+	u32 h = sl_hash(id) & mask;
+	for (;;)
+	{
+		u32 old = atomicCAS(&table_id[h], 0xffffffffu, id);
+		if (old == 0xffffffffu || old == id)
+			break;
+		h = (h + 1) & mask;
+	}
+	atomicMin(&table_first[h], u32(i));
+	slot_of[i] = h;
+}
+
+KERNEL k_sl_first_flags(const u32* __restrict__ slot_of, const u32* __restrict__ table_first, u32 n, u32* flags)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	flags[i] = table_first[slot_of[i]] == u32(i) ? 1u : 0u;
+}
+
+KERNEL k_sl_assign_cells(const u32* __restrict__ slot_of, const u32* __restrict__ table_first, const u32* __restrict__ first_rank, u32 n, u32* cells)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	cells[i] = first_rank[table_first[slot_of[i]]];
+}
+
+// (cell, corner) entries of fillCellQuadrics: one per corner, or one (weight 3) for a triangle inside a single cell
+KERNEL k_sl_quadric_entries(const u32* __restrict__ cells, u32 T, u32* entry_cell, u32* entry_corner)
+{
+	size_t t = GTID;
+	if (t >= T)
+		return;
+	u32 c0 = cells[t * 3 + 0], c1 = cells[t * 3 + 1], c2 = cells[t * 3 + 2];
+	bool single = (c0 == c1) & (c0 == c2);
+	entry_cell[t * 3 + 0] = c0;
+	entry_cell[t * 3 + 1] = single ? 0xffffffffu : c1;
+	entry_cell[t * 3 + 2] = single ? 0xffffffffu : c2;
+	entry_corner[t * 3 + 0] = u32(t * 3 + 0);
+	entry_corner[t * 3 + 1] = u32(t * 3 + 1);
+	entry_corner[t * 3 + 2] = u32(t * 3 + 2);
+}
+
+KERNEL k_sl_cell_heads(const u32* __restrict__ sorted_cell, u32 n, u32* cell_begin, u32 cell_count)
+{
+	size_t i = GTID;
+	if (i > n)
+		return;
+	u32 cur = i < n ? sorted_cell[i] : 0xffffffffu;
+	u32 prev = i > 0 ? sorted_cell[i - 1] : 0xffffffffu;
+	if (i == 0 || cur != prev)
+	{
+		if (cur != 0xffffffffu)
+			cell_begin[cur] = u32(i);
+		if (i > 0 && prev != 0xffffffffu && cur == 0xffffffffu)
+			cell_begin[cell_count] = u32(i); // end of the valid entries
+	}
+	if (i == n && prev != 0xffffffffu)
+		cell_begin[cell_count] = u32(n);
+}
+
+KERNEL k_sl_cell_quadrics(const u32* __restrict__ sorted_cell, const u32* __restrict__ sorted_corner, const u32* __restrict__ cell_begin, const u32* __restrict__ cells, const Vector3* __restrict__ vpos, u32 cell_count,
+    u32 valid_entries, Quadric* cell_quadrics)
+{
+	size_t c = GTID;
+	if (c >= cell_count)
+		return;
+	Quadric Q;
+	quadric_zero(Q);
+	for (u32 e = cell_begin[c]; e < valid_entries && sorted_cell[e] == u32(c); ++e)
+	{
+		u32 corner = sorted_corner[e];
+		u32 t = corner / 3;
+		u32 c0 = cells[t * 3 + 0], c1 = cells[t * 3 + 1], c2 = cells[t * 3 + 2];
+		bool single = (c0 == c1) & (c0 == c2);
+		Quadric R;
+		quadric_from_triangle(R, vpos[t * 3 + 0], vpos[t * 3 + 1], vpos[t * 3 + 2], single ? 3.f : 1.f);
+		quadric_add(Q, R);
+	}
+	cell_quadrics[c] = Q;
+}
+
+KERNEL k_sl_cell_remap(const u32* __restrict__ cells, const Quadric* __restrict__ cell_quadrics, const Vector3* __restrict__ vpos, u32 n, u64* cell_best)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	u32 cell = cells[i];
+	float error = quadric_error(cell_quadrics[cell], vpos[i]);
+	u64 key = (u64(__float_as_uint(error)) << 32) | u64(u32(i));
+	atomicMin(reinterpret_cast<unsigned long long*>(&cell_best[cell]), (unsigned long long)key);
+}
+
+KERNEL k_sl_max_error(const u64* __restrict__ cell_best, u32 cell_count, u32* max_bits)
+{
+	size_t c = GTID;
+	if (c >= cell_count)
+		return;
+	atomicMax(max_bits, u32(cell_best[c] >> 32));
+}
+
+// rotated (lowest corner id first) output triple per non-degenerate triangle; duplicates keep their first occurrence
+KERNEL k_sl_triangles(const u32* __restrict__ cells, const u64* __restrict__ cell_best, u32 T, u32* triple, u64* table_key, u32* table_first, u32 mask, u32* slot_of)
+{
+	size_t t = GTID;
+	if (t >= T)
+		return;
+	u32 c0 = cells[t * 3 + 0], c1 = cells[t * 3 + 1], c2 = cells[t * 3 + 2];
+	slot_of[t] = 0xffffffffu;
+	if (!(c0 != c1 && c0 != c2 && c1 != c2))
+		return;
+	u32 a = u32(cell_best[c0]), b = u32(cell_best[c1]), c = u32(cell_best[c2]);
+	if (b < a && b < c)
+	{
+		u32 tmp = a;
+		a = b, b = c, c = tmp;
+	}
+	else if (c < a && c < b)
+	{
+		u32 tmp = c;
+		c = b, b = a, a = tmp;
+	}
+	triple[t * 3 + 0] = a;
+	triple[t * 3 + 1] = b;
+	triple[t * 3 + 2] = c;
+	// corner ids of a group are < 2^21 (checked by the caller), so the triple packs exactly into one 64-bit key
+	u32 h = ((a * 73856093u) ^ (b * 19349663u) ^ (c * 83492791u)) & mask;
+	u64 key = (u64(a) << 42) | (u64(b) << 21) | u64(c);
+	for (;;)
+	{
+		u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&table_key[h]), ~0ull, (unsigned long long)key);
+		if (old == ~0ull || old == key)
+			break;
+		h = (h + 1) & mask;
+	}
+	atomicMin(&table_first[h], u32(t));
+	slot_of[t] = h;
+}
+
+KERNEL k_sl_keep_flags(const u32* __restrict__ slot_of, const u32* __restrict__ table_first, u32 T, u32* keep)
+{
+	size_t t = GTID;
+	if (t >= T)
+		return;
+	keep[t] = (slot_of[t] != 0xffffffffu && table_first[slot_of[t]] == u32(t)) ? 1u : 0u;
+}
+
+KERNEL k_sl_emit(const u32* __restrict__ triple, const u32* __restrict__ keep_scanned, u32 total, const u32* __restrict__ corner_vertex, u32 T, u32* out_tri)
+{
+	size_t t = GTID;
+	if (t >= T)
+		return;
+	u32 pos = keep_scanned[t];
+	u32 next = t + 1 < T ? keep_scanned[t + 1] : total;
+	if (next == pos)
+		return;
+	out_tri[pos * 3 + 0] = corner_vertex[triple[t * 3 + 0]];
+	out_tri[pos * 3 + 1] = corner_vertex[triple[t * 3 + 1]];
+	out_tri[pos * 3 + 2] = corner_vertex[triple[t * 3 + 2]];
+}
+
+// three point interpolation of the grid-size search (simplifier.cpp:2323-2329)
+static float sloppy_interpolate(float y, float x0, float y0, float x1, float y1, float x2, float y2)
+{
+	float num = (y1 - y) * (x1 - x2) * (x1 - x0) * (y2 - y0);
+	float den = (y2 - y) * (x1 - x2) * (y0 - y1) + (y0 - y) * (x1 - x0) * (y1 - y2);
+	return x1 + (den == 0.f ? 0.f : num / den);
+}
+
+// One group: corner_vertex = the group's merged index list (T triangles). Writes the simplified triangles (global vertex
+// ids) to out_tri (capacity T) and returns their count; *out_error = absolute error (before the sloppy error factor).
+static float host_uint_as_float(u32 u)
+{
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+
+static float host_float_from_order_key(u32 k)
+{
+	return host_uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+static u32 sloppy_group(const u32* corner_vertex, u32 T, u32 target_tris, const DeviceMesh& mesh, const u8* locks, u32* out_tri, float* out_error, Arena& temp)
+{
+	ArenaScope scope(temp);
+	u32 n = T * 3;
+	if (n >= (1u << 21))
+		throw Error("clodb200: sloppy fallback supports groups of up to 699050 triangles");
+	size_t target_index_count = size_t(target_tris) * 3;
+	size_t target_cell_count = target_index_count / 6;
+	u32* scalars = temp.alloc<u32>(8);
+
+	// rescalePositions over the de-indexed subset
+	u32 init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+	dev_h2d(scalars, init, sizeof(init));
+	LAUNCH(k_sl_minmax, n, corner_vertex, mesh.positions, n, scalars);
+	std::vector<u32> mm = dev_download(scalars, 6);
+	float minv[3], maxv[3];
+	for (int k = 0; k < 3; ++k)
+	{
+		minv[k] = host_float_from_order_key(mm[k]);
+		maxv[k] = host_float_from_order_key(mm[3 + k]);
+	}
+	float extent = 0.f;
+	for (int k = 0; k < 3; ++k)
+		extent = (maxv[k] - minv[k]) < extent ? extent : (maxv[k] - minv[k]);
+	float scale = extent == 0 ? 0.f : 1.f / extent;
+	Vector3* vpos = temp.alloc<Vector3>(n);
+	LAUNCH(k_sl_rescale, n, corner_vertex, mesh.positions, n, minv[0], minv[1], minv[2], scale, vpos);
+
+	u32* ids = temp.alloc<u32>(n);
+	auto count_triangles = [&](int grid) -> size_t {
+		LAUNCH(k_sl_ids, n, vpos, corner_vertex, locks, n, grid, ids);
+		dev_memset(scalars + 6, 0, sizeof(u32));
+		LAUNCH(k_sl_count_triangles, T, ids, T, scalars + 6);
+		return dev_read(scalars + 6);
+	};
+
+	// guided search for the grid size (target_error = FLT_MAX => min_grid = 1; locks are always passed)
+	const int kInterpolationPasses = 5;
+	int min_grid = 1;
+	int max_grid = 1025;
+	size_t min_triangles = count_triangles(min_grid);
+	size_t max_triangles = T;
+	int next_grid_size = int(sqrtf(float(target_cell_count)) + 0.5f);
+	for (int pass = 0; pass < 10 + kInterpolationPasses; ++pass)
+	{
+		if (min_triangles >= target_index_count / 3 || max_grid - min_grid <= 1)
+			break;
+		int grid_size = next_grid_size;
+		grid_size = (grid_size <= min_grid) ? min_grid + 1 : (grid_size >= max_grid ? max_grid - 1 : grid_size);
+		size_t triangles = count_triangles(grid_size);
+		float tip = sloppy_interpolate(float(size_t(target_index_count / 3)), float(min_grid), float(min_triangles), float(grid_size), float(triangles), float(max_grid), float(max_triangles));
+		if (triangles <= target_index_count / 3)
+		{
+			min_grid = grid_size;
+			min_triangles = triangles;
+		}
+		else
+		{
+			max_grid = grid_size;
+			max_triangles = triangles;
+		}
+		next_grid_size = (pass < kInterpolationPasses) ? int(tip + 0.5f) : (min_grid + max_grid) / 2;
+	}
+	if (min_triangles == 0)
+	{
+		*out_error = 1.f * extent;
+		return 0;
+	}
+
+	// cells in first-occurrence order
+	LAUNCH(k_sl_ids, n, vpos, corner_vertex, locks, n, min_grid, ids);
+	size_t table_size = 1;
+	while (table_size < size_t(n) * 2)
+		table_size <<= 1;
+	u32* table_id = temp.alloc<u32>(table_size);
+	u32* table_first = temp.alloc<u32>(table_size);
+	u32* slot_of = temp.alloc<u32>(n);
+	u32* flags = temp.alloc<u32>(size_t(n) + 1);
+	u32* cells = temp.alloc<u32>(n);
+	dev_memset(table_id, 0xff, table_size * 4);
+	dev_memset(table_first, 0xff, table_size * 4);
+	LAUNCH(k_sl_cell_insert, n, ids, n, table_id, table_first, u32(table_size - 1), slot_of);
+	LAUNCH(k_sl_first_flags, n, slot_of, table_first, n, flags);
+	exclusive_scan_u32(flags, flags, n, scalars + 6, temp);
+	u32 cell_count = dev_read(scalars + 6);
+	LAUNCH(k_sl_assign_cells, n, slot_of, table_first, flags, n, cells);
+
+	// per-cell quadrics, summed in ascending corner order
+	u32* entry_cell = temp.alloc<u32>(n);
+	u32* entry_corner = temp.alloc<u32>(n);
+	u32* entry_cell_tmp = temp.alloc<u32>(n);
+	u32* entry_corner_tmp = temp.alloc<u32>(n);
+	u32* cell_begin = temp.alloc<u32>(size_t(cell_count) + 1);
+	Quadric* cell_quadrics = temp.alloc<Quadric>(cell_count);
+	u64* cell_best = temp.alloc<u64>(cell_count);
+	LAUNCH(k_sl_quadric_entries, T, cells, T, entry_cell, entry_corner);
+	radix_sort_pairs<u32>(entry_cell, entry_cell_tmp, entry_corner, entry_corner_tmp, n, 0, 32, temp);
+	dev_memset(cell_begin, 0, (size_t(cell_count) + 1) * 4);
+	LAUNCH(k_sl_cell_heads, size_t(n) + 1, entry_cell, n, cell_begin, cell_count);
+	u32 valid_entries = dev_read(cell_begin + cell_count);
+	LAUNCH(k_sl_cell_quadrics, cell_count, entry_cell, entry_corner, cell_begin, cells, vpos, cell_count, valid_entries, cell_quadrics);
+
+	// best vertex per cell, error
+	dev_memset(cell_best, 0xff, size_t(cell_count) * 8);
+	LAUNCH(k_sl_cell_remap, n, cells, cell_quadrics, vpos, n, cell_best);
+	dev_memset(scalars + 7, 0, sizeof(u32));
+	LAUNCH(k_sl_max_error, cell_count, cell_best, cell_count, scalars + 7);
+
+	// triangles: drop degenerate and duplicate ones, keep order
+	size_t tt_size = 1;
+	while (tt_size < size_t(T) * 2)
+		tt_size <<= 1;
+	u32* triple = temp.alloc<u32>(n);
+	u64* tt_key = temp.alloc<u64>(tt_size);
+	u32* tt_first = temp.alloc<u32>(tt_size);
+	u32* tslot = temp.alloc<u32>(T);
+	u32* keep = temp.alloc<u32>(size_t(T) + 1);
+	dev_memset(tt_key, 0xff, tt_size * 8);
+	dev_memset(tt_first, 0xff, tt_size * 4);
+	LAUNCH(k_sl_triangles, T, cells, cell_best, T, triple, tt_key, tt_first, u32(tt_size - 1), tslot);
+	LAUNCH(k_sl_keep_flags, T, tslot, tt_first, T, keep);
+	exclusive_scan_u32(keep, keep, T, scalars + 6, temp);
+	u32 kept = dev_read(scalars + 6);
+	LAUNCH(k_sl_emit, T, triple, keep, kept, corner_vertex, T, out_tri);
+
+	float result_error = host_uint_as_float(dev_read(scalars + 7));
+	*out_error = sqrtf(result_error) * extent;
+	return kept;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 static void build_adjacency(const u32* idx, size_t corners, const u32* remap, u32 vertex_count, u32* adj_off, u32* adj_corner, bool sorted, Arena& temp)
 {
@@ -1938,6 +2329,51 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 	LAUNCH(k_finalize_output, size_t(cur_T) * 3, idx, sv_global, out.tri, size_t(cur_T) * 3);
 	LAUNCH(k_group_results, G, groups, group_extent, out.group_tri_offset, out.group_error, G);
 	out.triangle_count = cur_T;
+
+	// ---- sloppy fallback for groups that are still above their target (clusterlod.h:623-628)
+	if (config.simplify_fallback_sloppy)
+	{
+		std::vector<GroupState> gh = dev_download(groups, G);
+		bool any = false;
+		for (u32 g = 0; g < G; ++g)
+			any |= gh[g].tri_count > gh[g].target_tris;
+		if (any)
+		{
+			std::vector<u32> new_offset(size_t(G) + 1, 0);
+			std::vector<float> new_error = dev_download(out.group_error, G);
+			std::vector<u32*> sloppy_tri(G, nullptr);
+			std::vector<u32> sloppy_count(G, 0);
+			for (u32 g = 0; g < G; ++g)
+			{
+				u32 count = gh[g].tri_count;
+				if (count > gh[g].target_tris)
+				{
+					u32 Tg = group_tri_offset_host[g + 1] - group_tri_offset_host[g];
+					sloppy_tri[g] = temp.alloc<u32>(size_t(Tg) * 3); // lives until the scope of this call ends
+					float err = 0.f;
+					sloppy_count[g] = sloppy_group(gtri + size_t(group_tri_offset_host[g]) * 3, Tg, gh[g].target_tris, mesh, locks, sloppy_tri[g], &err, temp);
+					new_error[g] = err * config.simplify_error_factor_sloppy;
+					count = sloppy_count[g];
+					g_simplify_stats.sloppy_groups++;
+				}
+				new_offset[g + 1] = new_offset[g] + count;
+			}
+			// reassemble the level output group by group (the fallback may return more or fewer triangles)
+			u32* assembled = temp.alloc<u32>(size_t(new_offset[G]) * 3 + 3);
+			for (u32 g = 0; g < G; ++g)
+			{
+				u32 count = new_offset[g + 1] - new_offset[g];
+				const u32* src = sloppy_tri[g] ? sloppy_tri[g] : out.tri + size_t(gh[g].tri_begin) * 3;
+				dev_d2d(assembled + size_t(new_offset[g]) * 3, src, size_t(count) * 12);
+			}
+			if (size_t(new_offset[G]) > size_t(T))
+				throw Error("clodb200: sloppy fallback produced more triangles than its input");
+			dev_d2d(out.tri, assembled, size_t(new_offset[G]) * 12);
+			dev_h2d(out.group_tri_offset, new_offset.data(), (size_t(G) + 1) * 4);
+			dev_h2d(out.group_error, new_error.data(), size_t(G) * 4);
+			out.triangle_count = new_offset[G];
+		}
+	}
 	return out;
 }
 

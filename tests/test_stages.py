@@ -114,18 +114,13 @@ def test_simplify_groups_match_reference(lib, ref_dag, meshes, name):
     for level in range(dag.num_levels):
         mi, mo = dag.level(level, "merged_indices"), dag.level(level, "merged_offsets")
         si, so, se = lib.simplify_groups(m.positions, mi, mo, dag.level(level, "locks"), attributes=m.normals, attribute_weights=w)
-        # groups the reference finished with the sloppy fallback are out of scope of this entry point
         rso, rsi, rerr = dag.level(level, "simp_offsets"), dag.level(level, "simp_indices"), dag.level(level, "group_error")
         term = dag.level(level, "group_terminal").astype(bool)
         for g in range(len(mo) - 1):
             if term[g]:
                 continue
-            tin = (mo[g + 1] - mo[g]) // 3
             want = rsi[rso[g] : rso[g + 1]]
             got = si[so[g] : so[g + 1]]
-            target = max(1, int(np.float32(tin) * np.float32(0.5)))
-            if want.size // 3 > target:
-                continue  # reference needed the sloppy fallback for this group
             assert abs(got.size - want.size) <= 0.02 * want.size + 3, (level, g)
             assert se[g] <= rerr[g] * 1.05 + 1e-12, (level, g)
             assert np.array_equal(got, want), (level, g)
@@ -142,10 +137,8 @@ def _check_dag_simplify(lib, oracle, m, attrs, weights, protect):
         rso, rsi, rerr = dag.level(level, "simp_offsets"), dag.level(level, "simp_indices"), dag.level(level, "group_error")
         term = dag.level(level, "group_terminal").astype(bool)
         for g in range(len(mo) - 1):
-            tin = (mo[g + 1] - mo[g]) // 3
-            target = max(1, int(np.float32(tin) * np.float32(0.5)))
             want = rsi[rso[g] : rso[g + 1]]
-            if term[g] or want.size // 3 > target:
+            if term[g]:
                 continue
             got = si[so[g] : so[g + 1]]
             total += 1
@@ -170,3 +163,34 @@ def test_simplify_many_groups(lib, oracle):
     m = meshgen.grid(330, seed=11)  # ~218k triangles => 5 groups at depth 0
     exact, total = _check_dag_simplify(lib, oracle, m, m.normals, np.ones(3, np.float32), 7)
     assert total >= 8 and exact == total
+
+
+@pytest.mark.parametrize("name", ["grid64", "ico16uv", "torus"])
+def test_sloppy_fallback_bit_exact(lib, oracle, meshes, name):
+    """Groups whose edge collapse misses the target (here forced by locking random vertices) go through the sloppy
+    fallback (clusterlod.h:567-599 -> meshopt_simplifySloppy): same triangles, same error as the reference, also when
+    only some groups of a batched call need it."""
+    m = meshes[name]
+    T = m.indices.size // 3
+    w = np.ones(3, np.float32)
+    rng = np.random.default_rng(1)
+    used_fallback = 0
+    for p in (0.3, 0.6, 0.9, 1.0):
+        locks = (rng.random(len(m.positions)) < p).astype(np.uint8)
+        target = int(np.float32(T) * np.float32(0.5)) * 3
+        want, werr = oracle.simplify(m.positions, m.indices, locks, target, attributes=m.normals, attribute_weights=w)
+        cfg = oracle.builder_config()
+        cfg.simplify_fallback_sloppy = False
+        edge_only, _ = oracle.simplify(m.positions, m.indices, locks, target, attributes=m.normals, attribute_weights=w, config=cfg)
+        used_fallback += int(edge_only.size > target)
+        # batched call: group 0 = the whole mesh, group 1 = its first half (different target, usually no fallback at low p)
+        half = (T // 2) * 3
+        idx2 = np.concatenate([m.indices, m.indices[:half]])
+        offs = np.array([0, m.indices.size, m.indices.size + half], np.uint32)
+        si, so, se = lib.simplify_groups(m.positions, idx2, offs, locks, attributes=m.normals, attribute_weights=w)
+        assert np.array_equal(si[so[0] : so[1]], want), p
+        assert se[0] == np.float32(werr), p
+        want1, werr1 = oracle.simplify(m.positions, m.indices[:half], locks, int(np.float32(T // 2) * np.float32(0.5)) * 3, attributes=m.normals, attribute_weights=w)
+        assert np.array_equal(si[so[1] : so[2]], want1), p
+        assert se[1] == np.float32(werr1), p
+    assert used_fallback >= 2
