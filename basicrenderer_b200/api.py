@@ -133,6 +133,9 @@ class ClodLib:
         L.clodb200_recordFree.argtypes = [C.c_void_p]
         L.clodb200_buildEx.restype = C.c_size_t
         L.clodb200_buildEx.argtypes = [Config, MeshDesc, C.c_void_p, OUTPUT_EX, C.c_void_p]
+        from . import artifacts as _art
+
+        _art.bind(L)
         self._check(L.clodb200_init(device))
 
     def _check(self, status: int):
@@ -309,6 +312,63 @@ class ClodLib:
         if n == 0 and err:
             raise ClodbError(err)
         return n
+
+    # ---- outer boundary: BuildClusterLODArtifactsFromGeometry (ClusterLODUtilities.h:5-13) ------------------------------
+    def default_builder_settings(self):
+        return self._lib.clodb200_defaultBuilderSettings()
+
+    def _artifacts(self, handle, views: bool = False, keep_handle: bool = False):
+        from . import artifacts as _art
+
+        if not handle:
+            raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200 artifact build failed")
+        a = _art.collect(self._lib, handle, views=views)
+        if keep_handle:
+            a.handle = handle
+        else:
+            self._lib.clodb200_artifactsFree(handle)
+        return a
+
+    def build_artifacts(self, vertices, indices, flags, uv_sets=None, tangents=None, settings=None, views: bool = False, keep_handle: bool = False):
+        """Host arrays in, ClusterLODPrebuildArtifacts out (upload + DAG build + page encode + read-back)."""
+        from . import artifacts as _art
+
+        g, keep = _art.make_geometry(vertices, indices, flags, uv_sets, tangents)
+        st = settings or self.default_builder_settings()
+        return self._artifacts(self._lib.clodb200_buildArtifacts(C.byref(g), C.byref(st)), views=views, keep_handle=keep_handle)
+
+    def upload_geometry(self, vertices, indices, flags, uv_sets=None, tangents=None, settings=None):
+        from . import artifacts as _art
+
+        g, keep = _art.make_geometry(vertices, indices, flags, uv_sets, tangents)
+        st = settings or self.default_builder_settings()
+        h = self._lib.clodb200_geometryUpload(C.byref(g), C.byref(st))
+        if not h:
+            raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200 geometry upload failed")
+        return h
+
+    def free_geometry(self, handle):
+        self._lib.clodb200_geometryFree(handle)
+
+    def build_artifacts_resident(self, geometry_handle, views: bool = False, keep_handle: bool = False):
+        return self._artifacts(self._lib.clodb200_geometryBuildArtifacts(geometry_handle), views=views, keep_handle=keep_handle)
+
+    def free_artifacts(self, artifacts):
+        self._lib.clodb200_artifactsFree(artifacts.handle)
+        artifacts.handle = None
+
+    def save_cache(self, artifacts, directory: str, container_file_name: str, metadata_file_name: str, source_identifier: str = "", prim_path: str = "", subset_name: str = "",
+                   build_config_hash: int = 0):
+        """CLodCache::Save without the .usdc wrapper: <directory>/<container> (.clodbin) + <directory>/<metadata> (clodBlob bytes)."""
+        self._check(self._lib.clodb200_artifactsSaveCache(artifacts.handle, directory.encode(), container_file_name.encode(), metadata_file_name.encode(),
+                                                          source_identifier.encode(), prim_path.encode(), subset_name.encode(), build_config_hash))
+
+    def serialize_metadata(self, artifacts, container_file_name: str, source_identifier: str = "", prim_path: str = "", subset_name: str = "", build_config_hash: int = 0) -> bytes:
+        args = (artifacts.handle, container_file_name.encode(), source_identifier.encode(), prim_path.encode(), subset_name.encode(), build_config_hash)
+        n = self._lib.clodb200_artifactsSerializeMetadata(*args, None, 0)
+        buf = C.create_string_buffer(n)
+        self._lib.clodb200_artifactsSerializeMetadata(*args, buf, n)
+        return buf.raw
 
     def timer_start(self):
         self._lib.clodb200_timerStart()

@@ -2,6 +2,7 @@
 #include "../../include/clodb200.h"
 #include "clodb.h"
 #include "dag.h"
+#include "artifacts.h"
 
 #include <map>
 #include <algorithm>
@@ -828,6 +829,335 @@ void clodb200_recordFree(clodb200_record* record)
 	}
 	else
 		delete record;
+}
+
+// ---- outer boundary: BuildClusterLODArtifactsFromGeometry --------------------------------------------------------------
+struct clodb200_artifacts
+{
+	Artifacts data;
+};
+
+struct clodb200_device_geometry
+{
+	DeviceGeometry geometry;
+	BuilderSettings settings;
+	std::vector<DeviceBlock> allocations;
+};
+
+static clodb200_artifacts* g_artifacts_pool = nullptr; // one recycled result (keeps its pinned page buffer)
+
+static BuilderSettings to_settings(const clodb200_builder_settings* s)
+{
+	BuilderSettings r;
+	if (!s)
+		return r;
+	r.lod_error_merge_previous = s->lodErrorMergePrevious;
+	r.lod_error_merge_additive = s->lodErrorMergeAdditive;
+	r.partition_size_floor = s->partitionSizeFloor;
+	r.preserve_imported_normals = s->preserveImportedNormals != 0;
+	r.enable_normal_attribute_simplification = s->enableNormalAttributeSimplification != 0;
+	r.normal_attribute_weight = s->normalAttributeWeight;
+	r.simplify_tangent_weight = s->simplifyTangentWeight;
+	r.simplify_tangent_sign_weight = s->simplifyTangentSignWeight;
+	return r;
+}
+
+static bool geometry_is_buildable(const clodb200_geometry& g)
+{
+	// the conditions under which clodBuildEx returns 0 (clusterlod.h:796-816); the builder then returns empty artifacts
+	return g.vertices && g.indices && g.vertex_count > 0 && g.index_count > 0 && g.vertex_stride >= 12;
+}
+
+static clodb200_device_geometry* upload_geometry_locked(const clodb200_geometry& g, const clodb200_builder_settings* settings)
+{
+	if (g.index_count % 3 || g.vertex_stride % 4 || g.uv_set_count > kMaxUvSets || g.vertex_count >= 0xffffffffull || g.index_count / 3 >= 0xffffffffull)
+		throw Error("clodb200: index count must be a multiple of 3, the vertex stride a multiple of 4, at most 4 UV sets");
+	clodb200_device_geometry* dg = new clodb200_device_geometry();
+	try
+	{
+		dg->settings = to_settings(settings);
+		const BuilderSettings& st = dg->settings;
+		DeviceGeometry& geo = dg->geometry;
+		const size_t V = g.vertex_count;
+		u8* dv = static_cast<u8*>(block_alloc(V * g.vertex_stride, dg->allocations));
+		dev_h2d(dv, g.vertices, V * g.vertex_stride);
+		geo.vertices = dv;
+		geo.vertex_stride = g.vertex_stride;
+		geo.vertex_flags = g.vertex_flags;
+		geo.vertex_count = V;
+		u32* di = static_cast<u32*>(block_alloc(g.index_count * 4, dg->allocations));
+		dev_h2d(di, g.indices, g.index_count * 4);
+		geo.indices = di;
+		geo.index_count = g.index_count;
+		u32* bad = static_cast<u32*>(block_alloc(sizeof(u32), dg->allocations));
+		dev_memset(bad, 0, sizeof(u32));
+		LAUNCH(k_index_range, g.index_count, di, g.index_count, u32(V), bad);
+		if (dev_read(bad))
+			throw Error("clodb200: index out of range");
+
+		geo.uv_set_count = u32(g.uv_set_count);
+		for (size_t s = 0; s < g.uv_set_count; ++s)
+		{
+			float* duv = static_cast<float*>(block_alloc(V * 8, dg->allocations));
+			if (g.uv_sets[s].values && g.uv_sets[s].count == V)
+				dev_h2d(duv, g.uv_sets[s].values, V * 8);
+			else
+				dev_memset(duv, 0, V * 8);
+			geo.uv_values[s] = duv;
+			geo.uv_stride[s] = 2;
+		}
+
+		// simplification attribute stream (ClusterLODUtilities.cpp:5359-5410): normals x3, then tangent xyz + sign
+		const bool has_normals = (g.vertex_flags & kVertexNormals) != 0 && g.vertex_stride >= 24;
+		const bool has_texcoords = (g.vertex_flags & kVertexTexcoords) != 0 && g.vertex_stride >= 32;
+		const bool use_normals = st.enable_normal_attribute_simplification && has_normals;
+		const bool wants_tangents = use_normals && has_texcoords;
+		if (wants_tangents && !g.tangents)
+			throw Error("clodb200: a vertex stream with normals and texcoords needs the MikkTSpace tangent stream (clodb200_geometry::tangents); tangent generation is not built in");
+		DeviceMesh& mesh = geo.mesh;
+		float* dpos = static_cast<float*>(block_alloc(V * 12, dg->allocations));
+		u32 acount = (use_normals ? 3u : 0u) + (wants_tangents ? 4u : 0u);
+		float* dattr = acount ? static_cast<float*>(block_alloc(V * acount * 4, dg->allocations)) : nullptr;
+		float* dtan = nullptr;
+		if (wants_tangents)
+		{
+			dtan = static_cast<float*>(block_alloc(V * 16, dg->allocations));
+			dev_h2d(dtan, g.tangents, V * 16);
+		}
+		split_vertex_streams(dv, g.vertex_stride, V, dpos, dattr, acount, use_normals, dtan);
+		mesh.positions = dpos;
+		mesh.vertex_count = V;
+		if (acount)
+		{
+			mesh.attributes = dattr;
+			mesh.attribute_stride = acount;
+			mesh.attribute_count = acount;
+			u32 k = 0;
+			if (use_normals)
+			{
+				float w = std::max(0.0f, st.normal_attribute_weight);
+				mesh.attribute_weights[0] = mesh.attribute_weights[1] = mesh.attribute_weights[2] = w;
+				mesh.attribute_protect_mask |= 7u << k;
+				k += 3;
+			}
+			if (wants_tangents)
+			{
+				float w = std::max(0.0f, st.simplify_tangent_weight);
+				mesh.attribute_weights[k] = mesh.attribute_weights[k + 1] = mesh.attribute_weights[k + 2] = w;
+				mesh.attribute_weights[k + 3] = std::max(0.0f, st.simplify_tangent_sign_weight);
+				mesh.attribute_protect_mask |= 15u << k;
+			}
+		}
+	}
+	catch (...)
+	{
+		block_release(dg->allocations);
+		delete dg;
+		throw;
+	}
+	return dg;
+}
+
+static void free_geometry_locked(clodb200_device_geometry* dg)
+{
+	if (!dg)
+		return;
+	block_release(dg->allocations);
+	delete dg;
+}
+
+static clodb200_artifacts* take_artifacts()
+{
+	clodb200_artifacts* a = g_artifacts_pool ? g_artifacts_pool : new clodb200_artifacts();
+	g_artifacts_pool = nullptr;
+	a->data.blobs.clear();
+	a->data.page_bytes = 0;
+	return a;
+}
+
+static clodb200_artifacts* build_artifacts_locked(const clodb200_device_geometry* dg)
+{
+	clodb200_artifacts* a = take_artifacts();
+	try
+	{
+		size_t T = dg->geometry.index_count / 3, V = dg->geometry.vertex_count;
+		size_t scale_temp = 640, scale_persist = 96;
+		if (const char* e = getenv("CLODB200_TEMP_BYTES_PER_TRI"))
+			scale_temp = size_t(atoll(e));
+		ensure_workspace(T * scale_persist + V * 32 + (64u << 20), T * scale_temp + V * 16 + (64u << 20));
+		build_artifacts(dg->geometry, dg->settings, g_ws, a->data, g_last_build_stats);
+		a->data.stats[12] = g_launches;
+	}
+	catch (...)
+	{
+		a->data.pages.destroy();
+		delete a;
+		throw;
+	}
+	return a;
+}
+
+clodb200_builder_settings clodb200_defaultBuilderSettings(void)
+{
+	clodb200_builder_settings s;
+	s.lodErrorMergePrevious = 1.5f;
+	s.lodErrorMergeAdditive = 0.0f;
+	s.partitionSizeFloor = 8u;
+	s.preserveImportedNormals = 1;
+	s.enableNormalAttributeSimplification = 1;
+	s.normalAttributeWeight = 1.0f;
+	s.simplifyTangentWeight = 0.01f;
+	s.simplifyTangentSignWeight = 0.5f;
+	return s;
+}
+
+clodb200_device_geometry* clodb200_geometryUpload(const clodb200_geometry* geometry, const clodb200_builder_settings* settings)
+{
+	clodb200_device_geometry* dg = nullptr;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!geometry || !geometry_is_buildable(*geometry))
+			return fail(CLODB200_ERR_INVALID, "clodb200: invalid or empty geometry");
+		dg = upload_geometry_locked(*geometry, settings);
+		return CLODB200_OK;
+	});
+	return dg;
+}
+
+void clodb200_geometryFree(clodb200_device_geometry* geometry)
+{
+	guarded([&]() -> int {
+		free_geometry_locked(geometry);
+		return CLODB200_OK;
+	});
+}
+
+clodb200_artifacts* clodb200_geometryBuildArtifacts(const clodb200_device_geometry* geometry)
+{
+	clodb200_artifacts* a = nullptr;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!geometry)
+			return fail(CLODB200_ERR_INVALID, "clodb200_geometryBuildArtifacts: null geometry");
+		a = build_artifacts_locked(geometry);
+		return CLODB200_OK;
+	});
+	return a;
+}
+
+clodb200_artifacts* clodb200_buildArtifacts(const clodb200_geometry* geometry, const clodb200_builder_settings* settings)
+{
+	clodb200_artifacts* a = nullptr;
+	guarded([&]() -> int {
+		t_last_error.clear();
+		if (!geometry)
+			return fail(CLODB200_ERR_INVALID, "clodb200_buildArtifacts: null geometry");
+		if (!geometry_is_buildable(*geometry))
+		{
+			// clodBuildEx returns 0 and the builder hands back empty artifacts (ClusterLODUtilities.cpp:4608-4609)
+			a = take_artifacts();
+			return CLODB200_OK;
+		}
+		clodb200_device_geometry* dg = upload_geometry_locked(*geometry, settings);
+		try
+		{
+			a = build_artifacts_locked(dg);
+		}
+		catch (...)
+		{
+			free_geometry_locked(dg);
+			throw;
+		}
+		free_geometry_locked(dg);
+		return CLODB200_OK;
+	});
+	return a;
+}
+
+int clodb200_artifactsGet(const clodb200_artifacts* artifacts, const char* name, const void** out_ptr, size_t* out_bytes)
+{
+	*out_ptr = nullptr;
+	*out_bytes = 0;
+	if (!artifacts || !name)
+		return 0;
+	if (!strcmp(name, "meshPages"))
+	{
+		*out_ptr = artifacts->data.pages.base;
+		*out_bytes = artifacts->data.page_bytes;
+		return 1;
+	}
+	if (!strcmp(name, "stats"))
+	{
+		*out_ptr = artifacts->data.stats;
+		*out_bytes = sizeof(artifacts->data.stats);
+		return 1;
+	}
+	auto it = artifacts->data.blobs.find(name);
+	if (it == artifacts->data.blobs.end())
+		return 0;
+	*out_ptr = it->second.data();
+	*out_bytes = it->second.size();
+	return 1;
+}
+
+void clodb200_artifactsFree(clodb200_artifacts* artifacts)
+{
+	if (!artifacts)
+		return;
+	std::lock_guard<std::mutex> lock(g_api_mutex);
+	if (!g_artifacts_pool)
+		g_artifacts_pool = artifacts;
+	else
+	{
+		artifacts->data.pages.destroy();
+		delete artifacts;
+	}
+}
+
+size_t clodb200_artifactsSerializeMetadata(const clodb200_artifacts* artifacts, const char* container_file_name, const char* source_identifier, const char* prim_path,
+    const char* subset_name, uint64_t build_config_hash, void* buffer, size_t capacity)
+{
+	if (!artifacts || artifacts->data.blobs.find("counts") == artifacts->data.blobs.end())
+		return 0;
+	CacheIdentity id;
+	id.source_identifier = source_identifier ? source_identifier : "";
+	id.prim_path = prim_path ? prim_path : "";
+	id.subset_name = subset_name ? subset_name : "";
+	id.build_config_hash = build_config_hash;
+	std::vector<u8> blob = serialize_cache_metadata(artifacts->data, id, container_file_name ? container_file_name : "");
+	if (buffer && capacity)
+		memcpy(buffer, blob.data(), std::min(capacity, blob.size()));
+	return blob.size();
+}
+
+int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char* directory, const char* container_file_name, const char* metadata_file_name,
+    const char* source_identifier, const char* prim_path, const char* subset_name, uint64_t build_config_hash)
+{
+	try
+	{
+		if (!artifacts || !directory || !container_file_name || !metadata_file_name || artifacts->data.blobs.find("counts") == artifacts->data.blobs.end())
+			return fail(CLODB200_ERR_INVALID, "clodb200_artifactsSaveCache: null argument or empty artifacts");
+		CacheIdentity id;
+		id.source_identifier = source_identifier ? source_identifier : "";
+		id.prim_path = prim_path ? prim_path : "";
+		id.subset_name = subset_name ? subset_name : "";
+		id.build_config_hash = build_config_hash;
+		std::string dir(directory);
+		write_cache_container(artifacts->data, dir + "/" + container_file_name);
+		std::vector<u8> blob = serialize_cache_metadata(artifacts->data, id, container_file_name);
+		FILE* f = fopen((dir + "/" + metadata_file_name).c_str(), "wb");
+		if (!f)
+			return fail(CLODB200_ERR_RUNTIME, "clodb200: cannot open the metadata file");
+		size_t written = fwrite(blob.data(), 1, blob.size(), f);
+		fclose(f);
+		if (written != blob.size())
+			return fail(CLODB200_ERR_RUNTIME, "clodb200: short write of the metadata file");
+		return CLODB200_OK;
+	}
+	catch (const std::exception& e)
+	{
+		return fail(CLODB200_ERR_RUNTIME, e.what());
+	}
 }
 
 #ifndef CLODB_EMU

@@ -72,18 +72,19 @@ struct LevelHost
 	const u32* vcount = nullptr;
 };
 
-static LevelHost download_level_async(const ClusterSet& cs, Workspace& ws, BuildStats& stats)
+static LevelHost download_level_async(const ClusterSet& cs, Workspace& ws, BuildStats& stats, bool with_indices)
 {
-	size_t tri_bytes = size_t(cs.triangle_count) * 12, off_bytes = (size_t(cs.cluster_count) + 1) * 4, vc_bytes = size_t(cs.cluster_count) * 4;
+	size_t tri_bytes = with_indices ? size_t(cs.triangle_count) * 12 : 0, off_bytes = (size_t(cs.cluster_count) + 1) * 4, vc_bytes = size_t(cs.cluster_count) * 4;
 	size_t off_at = (tri_bytes + 255) & ~size_t(255), vc_at = (off_at + off_bytes + 255) & ~size_t(255);
 	ws.stage.reserve(vc_at + vc_bytes + 256);
 	char* base = ws.stage.base;
-	dev_d2h_async(base, cs.tri, tri_bytes);
+	if (tri_bytes)
+		dev_d2h_async(base, cs.tri, tri_bytes);
 	dev_d2h_async(base + off_at, cs.cluster_tri_offset, off_bytes);
 	dev_d2h_async(base + vc_at, cs.cluster_vertex_count, vc_bytes);
 	stats.d2h_bytes += tri_bytes + off_bytes + vc_bytes;
 	LevelHost h;
-	h.tri = reinterpret_cast<const u32*>(base);
+	h.tri = with_indices ? reinterpret_cast<const u32*>(base) : nullptr;
 	h.off = reinterpret_cast<const u32*>(base + off_at);
 	h.vcount = reinterpret_cast<const u32*>(base + vc_at);
 	return h;
@@ -99,6 +100,8 @@ static size_t emit_level(const ClusterSet& cs, const LevelHost& host, const std:
 	const u32* vcount = host.vcount;
 
 	std::vector<DagCluster> out;
+	sink.begin_level(cs, depth);
+	sink.level_cluster_tri_offset = off;
 	group_ids.assign(groups.group_count, -1);
 	for (u32 g = 0; g < groups.group_count; ++g)
 	{
@@ -117,7 +120,7 @@ static size_t emit_level(const ClusterSet& cs, const LevelHost& host, const std:
 			dc.bounds[2] = src[2];
 			dc.bounds[3] = src[3];
 			dc.bounds[4] = bounds5[size_t(c) * 5 + 4];
-			dc.indices = tri + size_t(off[c]) * 3;
+			dc.indices = tri ? tri + size_t(off[c]) * 3 : nullptr;
 			dc.index_count = size_t(off[c + 1] - off[c]) * 3;
 			dc.vertex_count = vcount[c];
 		}
@@ -125,6 +128,7 @@ static size_t emit_level(const ClusterSet& cs, const LevelHost& host, const std:
 		dg.depth = depth;
 		for (int k = 0; k < 5; ++k)
 			dg.simplified[k] = group_bounds5[size_t(g) * 5 + k];
+		sink.cluster_ids = &group_clusters[b];
 		group_ids[g] = sink.group(dg, out.data(), out.size(), g);
 		stats.groups++;
 	}
@@ -148,7 +152,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 	// initial clusterization + precise bounds (clusterlod.h:844-848)
 	u32 seg0[2] = {0, T0};
 	ClusterSet level = clusterize(indices_dev, T0, seg0, 1, mesh.positions, config, ws);
-	LevelHost level_host = download_level_async(level, ws, stats);
+	LevelHost level_host = download_level_async(level, ws, stats, sink.wants_indices());
 	size_t total_clusters = level.cluster_count;
 
 	float* bounds4 = persist.alloc<float>(size_t(level.cluster_count) * 4);
@@ -267,7 +271,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		}
 
 		ClusterSet next = clusterize(next_tri, T_next, seg_dst.data(), S, mesh.positions, config, ws);
-		level_host = download_level_async(next, ws, stats);
+		level_host = download_level_async(next, ws, stats, sink.wants_indices());
 		total_clusters += next.cluster_count;
 
 		// clusters inherit the refined id and the bounds of the group they came from (clusterlod.h:919-925)

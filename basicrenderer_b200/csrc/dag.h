@@ -28,6 +28,19 @@ struct DagSink
 	virtual ~DagSink() {}
 	// returns the id stored as `refined` for clusters produced from this group
 	virtual int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t task_index) = 0;
+	// false: the level's index lists stay on the device (DagCluster::indices is null); the sink reads them from the
+	// ClusterSet handed to begin_level, whose arrays live in the persist arena until the build ends
+	virtual bool wants_indices() const
+	{
+		return true;
+	}
+	virtual void begin_level(const ClusterSet& /*level*/, int /*depth*/)
+	{
+	}
+	// set by the driver before every group(): ids (inside the level) of the clusters passed, and the level's
+	// cluster -> first triangle table (host copy)
+	const u32* cluster_ids = nullptr;
+	const u32* level_cluster_tri_offset = nullptr;
 };
 
 struct BuildStats

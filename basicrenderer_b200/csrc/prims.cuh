@@ -14,6 +14,7 @@ namespace clodb
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef uint8_t u8;
+typedef uint16_t u16;
 
 // --------------------------------------------------------------------------------------------------- small kernels
 template <typename T>

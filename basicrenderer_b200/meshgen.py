@@ -10,8 +10,8 @@ import os
 
 import numpy as np
 
-VERTEX_NORMALS = 1 << 0  # BasicRenderer/include/Mesh/VertexFlags.h
-VERTEX_TEXCOORDS = 1 << 1
+VERTEX_NORMALS = 1 << 1  # BasicRenderer/include/Mesh/VertexFlags.h (VERTEX_COLORS = 1 << 0)
+VERTEX_TEXCOORDS = 1 << 2
 
 
 class Mesh:

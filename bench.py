@@ -8,8 +8,11 @@ A step is one full DAG build of the workload mesh (N = 1: config C2, the 10 M-tr
 torchrun (N > 1) every rank builds its own shard of a scene batch of independent meshes (config C4 shape, weak scaling);
 there is no data-path collective, only the barrier and the max-over-ranks of the timing.
 
-`value` is timed with inputs resident in HBM; `e2e` goes through the host-pointer C ABI (clodb200_buildEx-shaped call:
-upload + build + read-back of the whole callback stream) from pinned host buffers.
+A build is the reference's outer builder call (BuildClusterLODArtifactsFromGeometry, ClusterLODUtilities.cpp:5325, mesh
+mode): DAG to a single root cluster + group tables + traversal hierarchy + mesh-wide page packing, finished
+ClusterLODPrebuiltData and page blobs in host memory. `value` is timed with the geometry resident in HBM
+(clodb200_geometryBuildArtifacts); `e2e` goes through the host-pointer C ABI (clodb200_buildArtifacts: upload + build +
+page read-back) from pinned host buffers.
 """
 from __future__ import annotations
 
@@ -55,6 +58,18 @@ KERNEL_BYTES_PER_THREAD = {
     # chained single-pass scan, 8 u32 elements per thread, read once + written once
     "(k_scan_chained<T, Op>)": 8 * 8,
 }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), for the
+# largest launch of the kernel on this workload; compare with roofline.algorithmic_bytes_per_launch of the same launch size
+KERNEL_DRAM_TRAFFIC = {}
+KERNEL_DRAM_TRAFFIC_SOURCE = None
+try:
+    _t = json.load(open(os.path.join(ROOT, "profiles", "kernel_dram_traffic.json")))
+    KERNEL_DRAM_TRAFFIC = _t.get("kernels", {})
+    KERNEL_DRAM_TRAFFIC_SOURCE = _t.get("source")
+except Exception:
+    pass
 
 
 def _sample_clocks(stop_event, out):
@@ -123,9 +138,11 @@ def run_ours(args):
     lib = load(local)
     mesh = _workload(rank, world)
     T = mesh.triangle_count
-    positions = _pin(mesh.positions.copy())
-    normals = _pin(mesh.normals.copy())
+    from basicrenderer_b200 import artifacts as art
+
+    vertices = _pin(art.interleave(mesh.positions, mesh.normals))
     indices = _pin(mesh.indices)
+    flags = art.VERTEX_NORMALS
 
     def barrier():
         if world > 1:
@@ -133,9 +150,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- resident-input timing (value)
-    handle = lib.upload_mesh(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK)
+    handle = lib.upload_geometry(vertices, indices, flags)
     for _ in range(args.warmup):
-        rec = lib.build_dag_resident(handle, keep_indices=False)
+        rec = lib.build_artifacts_resident(handle, views=True)
     stop = threading.Event()
     clock_samples = []
     sampler = threading.Thread(target=_sample_clocks, args=(stop, clock_samples), daemon=True)
@@ -144,10 +161,13 @@ def run_ours(args):
     launches0 = lib.launch_count
     lib.timer_start()
     for _ in range(args.steps):
-        rec = lib.build_dag_resident(handle, keep_indices=False)
+        rec = lib.build_artifacts_resident(handle, views=True, keep_handle=world > 1)
         if world > 1:
-            # the path's only exchange: per-mesh metadata to every rank (NCCL all-gather of sizes + padded blobs)
-            gathered = sharding.gather_metadata([rank], [sharding.dag_summary_blob(rec)])
+            # the path's only exchange: per-mesh cache metadata (SerializeMetadata bytes) to every rank (NCCL all-gather of
+            # sizes + padded blobs); the page payloads stay with the rank that built them
+            blob = lib.serialize_metadata(rec, f"clod_mesh{rank}.clodbin", "bench", f"/mesh{rank}")
+            lib.free_artifacts(rec)
+            gathered = sharding.gather_metadata([rank], [blob])
             assert len(gathered) == world
     ms = lib.timer_stop_ms()
     launches = lib.launch_count - launches0
@@ -155,17 +175,17 @@ def run_ours(args):
     stop.set()
     sampler.join()
 
-    # ---- end to end through the host-pointer C ABI (upload + build + read-back every step)
+    # ---- end to end through the host-pointer C ABI (upload + build + page read-back every step)
     for _ in range(min(args.warmup, 2)):
-        lib.build_dag(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK, views=True)
+        lib.build_artifacts(vertices, indices, flags, views=True)
     barrier()
     lib.timer_start()
     for _ in range(args.steps):
-        rec_e2e = lib.build_dag(positions, indices, attributes=normals, attribute_weights=ATTR_WEIGHTS, protect_mask=PROTECT_MASK, views=True)
+        rec_e2e = lib.build_artifacts(vertices, indices, flags, views=True)
     ms_e2e = lib.timer_stop_ms()
     barrier()
-    h2d = positions.nbytes + normals.nbytes + indices.nbytes
-    d2h = int(rec_e2e.stats[4])
+    h2d = vertices.nbytes + indices.nbytes
+    d2h = int(rec_e2e.stat["d2h_bytes"])
 
     # ---- max over ranks
     if world > 1:
@@ -182,7 +202,7 @@ def run_ours(args):
     if rank == 0:
         # ---- per-kernel breakdown of one more step, CUDA events on the build stream (not part of the timed region)
         lib.profile_enable(True)
-        lib.build_dag_resident(handle, keep_indices=False)
+        lib.build_artifacts_resident(handle, views=True)
         rows = lib.profile_report()
         lib.profile_enable(False)
         total_kernel_ms = sum(r[2] for r in rows)
@@ -207,7 +227,9 @@ def run_ours(args):
             "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
             "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None,
-            "traffic": None,
+            "traffic": KERNEL_DRAM_TRAFFIC.get(top[0]),
+            "traffic_source": KERNEL_DRAM_TRAFFIC_SOURCE if top[0] in KERNEL_DRAM_TRAFFIC else None,
+            "algorithmic_bytes_per_launch": (bpt * top[3] / max(1, top[1])) if bpt else None,
             "kernel_share_of_step": top[2] / total_kernel_ms if total_kernel_ms else None,
             "launches": top[1],
             "avg_launch_us": top[2] * 1e3 / max(1, top[1]),
@@ -235,10 +257,14 @@ def run_ours(args):
                 "workload": f"C2: {T}-triangle displaced heightfield grid (n={int(round((T / 2) ** 0.5))}), pos+normal, full DAG to a single root cluster" + ("" if world == 1 else f"; one such mesh per GPU ({world} independent meshes, sharded by mesh)"),
                 "builder": "clodDefaultConfig(128) + BasicRenderer overrides (128/128/64, partition 384, 8 refined ids, spatial clusters)",
                 "l2": "inputs and per-level working sets (>= 240 MB) exceed the 126 MB L2; no explicit flush",
-                "levels": int(rec.levels),
-                "groups": int(rec.groups),
-                "clusters": int(rec.total_clusters),
-                "scope": "clodBuildEx path (remap, clusterize, partition, lock, simplify, bounds, error rule, callback stream to host)",
+                "levels": rec.stat["levels"],
+                "groups": rec.stat["groups"],
+                "clusters": rec.stat["meshlets"],
+                "segments": rec.stat["segments"],
+                "pages": rec.stat["pages"],
+                "page_bytes": rec.stat["page_bytes"],
+                "scope": "BuildClusterLODArtifactsFromGeometry, mesh mode: remap, clusterize, partition, lock, simplify, bounds, error rule, group tables, traversal hierarchy, mesh page packing, page blobs read back to host",
+                "whole_job_roofline": _whole_job_roofline(rec.stat, T, ms / args.steps, peak),
             },
             "clocks": _clock_summary(clock_samples),
             "e2e": {"value": e2e_value, "unit": "Mtris/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
@@ -246,12 +272,20 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-    lib.free_mesh(handle)
+    lib.free_geometry(handle)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if result is not None:
         print(json.dumps(result))
+
+
+def _whole_job_roofline(stat, T0, ms_per_step, peak_gbs):
+    """compulsory bytes of the whole build from the builder's own output sums,
+    B = 24*sum T_l + S_v*sum V_l + 12*sum T_{l+1} + page bytes (S_v = 24 B for pos+normal)."""
+    b = 24 * stat["level_triangles"] + 24 * stat["group_vertices"] + 12 * stat["simplified_triangles"] + stat["page_bytes"]
+    gbs = b / (ms_per_step * 1e-3) / 1e9
+    return {"algorithmic_bytes": int(b), "bytes_per_input_triangle": b / T0, "achieved_gbs": gbs, "frac": gbs / peak_gbs}
 
 
 def _reference_sample_mesh():
@@ -260,21 +294,37 @@ def _reference_sample_mesh():
     return meshgen.grid(n, seed=1234)
 
 
-def cpu_baseline_sample():
-    """The compiled reference (oracle/_ref, clodBuildEx with its per-group tasks on all host threads) on a bounded
-    sample of the workload; reported, not a target."""
-    try:
-        from oracle import clodref
+def _reference_build(m, threads):
+    """One call of the reference's own builder (oracle/_ref/libclodref_full.so: the unmodified
+    BuildClusterLODArtifactsFromGeometry with its own clodBuildEx, mesh mode) on host arrays; returns seconds inside the call."""
+    from oracle import clodfull
 
-        if not clodref.available():
-            return {"value": None, "unit": "Mtris/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libclodref.so missing"}
+    v = clodfull.interleave(m.positions, m.normals)
+    return clodfull.build(v, m.indices, flags=clodfull.VERTEX_NORMALS, threads=threads).seconds
+
+
+def _reference_sample_text(m, threads, dt):
+    return (f"{m.triangle_count}-triangle tile of the C2 heightfield (same generator/density; the reference is ~80 % serial, so Mtris/s is size "
+            f"independent to first order), unmodified BuildClusterLODArtifactsFromGeometry in mesh mode (meshoptimizer v1.0 + clusterlod.h + L3 builder, "
+            f"std::thread pool of {threads} in place of oneTBB), {dt:.2f} s per build; includes the reference's unused VoxelSourceTriangleBVH::Build (SURVEY.md §8a a20)")
+
+
+def cpu_baseline_sample():
+    """The compiled reference on a bounded sample of the workload; reported, not a target."""
+    try:
+        from oracle import clodfull, clodref
+
+        if not clodfull.available():
+            return {"value": None, "unit": "Mtris/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libclodref_full.so missing"}
         m = _reference_sample_mesh()
         threads = os.cpu_count() or 1
-        t0 = time.perf_counter()
-        clodref.dag_build_timed(m.positions, m.indices, m.normals, ATTR_WEIGHTS, PROTECT_MASK, threads=threads)
-        dt = time.perf_counter() - t0
-        return {"value": m.triangle_count / dt / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "reference",
-                "sample": f"{m.triangle_count}-triangle tile of the C2 heightfield (same generator/density), reference clodBuildEx, {threads} threads, {dt:.2f} s"}
+        dt = _reference_build(m, threads)
+        out = {"value": m.triangle_count / dt / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "reference", "sample": _reference_sample_text(m, threads, dt)}
+        if clodref.available():
+            t0 = time.perf_counter()
+            clodref.dag_build_timed(m.positions, m.indices, m.normals, ATTR_WEIGHTS, PROTECT_MASK, threads=threads)
+            out["clodBuildEx_only_mtris_s"] = m.triangle_count / (time.perf_counter() - t0) / 1e6
+        return out
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": "Mtris/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -283,18 +333,16 @@ def run_reference(args):
     rank, world, _ = _dist()
     if rank != 0:
         return
-    from oracle import clodref
-
     m = _reference_sample_mesh()
     threads = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
-        clodref.dag_build_timed(m.positions, m.indices, m.normals, ATTR_WEIGHTS, PROTECT_MASK, threads=threads)
-    t0 = time.perf_counter()
+        _reference_build(m, threads)
+    total = 0.0
     for _ in range(args.steps):
-        clodref.dag_build_timed(m.positions, m.indices, m.normals, ATTR_WEIGHTS, PROTECT_MASK, threads=threads)
-    dt = (time.perf_counter() - t0) / args.steps
+        total += _reference_build(m, threads)
+    dt = total / args.steps
     value = m.triangle_count / dt / 1e6
-    sample = f"{m.triangle_count}-triangle tile of the C2 heightfield per step (bounded sample of the 10 M workload; the reference is ~80 % serial so Mtris/s is size independent to first order)"
+    sample = _reference_sample_text(m, threads, dt)
     print(json.dumps({
         "impl": "reference",
         "metric": "Mtris/s full cluster-LOD DAG build",
@@ -309,7 +357,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32+u32",
         "data": "synthetic",
-        "config": {"workload": "C2 heightfield, reference clodBuildEx (meshoptimizer v1.0 + clusterlod.h) on host cores", "sample": sample},
+        "config": {"workload": "C2 heightfield, reference BuildClusterLODArtifactsFromGeometry (mesh mode) on host cores", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -15,6 +15,8 @@
  *   clodb200_localIndices           <- clodLocalIndices, clusterlod.h:184 (implementation :972-1023)
  *   clodb200_lockBoundary           <- clod::lockBoundary, clusterlod.h:512-559
  *   clodb200_simplifyGroups         <- clod::simplify, clusterlod.h:601-659 (meshopt_simplifyWithAttributes per group)
+ *   clodb200_buildArtifacts         <- BuildClusterLODArtifactsFromGeometry, BasicRenderer/include/Mesh/ClusterLODUtilities.h:5-13
+ *   clodb200_artifactsSaveCache     <- CLodCache::Save (container + metadata blob), BasicRenderer/src/Import/CLodCache.cpp:512-583
  */
 #ifndef CLODB200_H
 #define CLODB200_H
@@ -176,6 +178,92 @@ clodb200_record* clodb200_buildRecorded(clodb200_config config, clodb200_mesh me
 clodb200_record* clodb200_meshBuildRecorded(clodb200_config config, const clodb200_device_mesh* mesh, int keep_indices);
 int clodb200_recordGet(const clodb200_record* record, const char* name, const void** out_ptr, size_t* out_bytes);
 void clodb200_recordFree(clodb200_record* record);
+
+/* ---- outer boundary: drop-in for BuildClusterLODArtifactsFromGeometry ------------------------------------------------
+ * Reference: BasicRenderer/include/Mesh/ClusterLODUtilities.h:5-13 (implementation src/Mesh/ClusterLODUtilities.cpp:5325-5766),
+ * i.e. MeshIngestBuilder::BuildClusterLODArtifacts() (ClusterLODTypes.h:415). The DAG build, the group output tables
+ * (:856-1805), the traversal hierarchy (:4606-4963) and the mesh-wide page packing (:2313-2540) run inside this call; the
+ * page blobs are written by the GPU and read back once. */
+
+/* The ClusterLODBuilderSettings fields that are live in mesh mode (ClusterLODTypes.h:187-212). The voxel fallback is not
+ * built: the call behaves as enableVoxelFallback = false / voxelFallbackMode = MeshOnly (CLodCacheTool --clod-voxel-mode=mesh).
+ * preserveImportedNormals = 0 is rejected (group normal recomputation is not implemented). */
+typedef struct clodb200_builder_settings
+{
+	float lodErrorMergePrevious;
+	float lodErrorMergeAdditive;
+	uint32_t partitionSizeFloor;
+	int preserveImportedNormals;
+	int enableNormalAttributeSimplification;
+	float normalAttributeWeight;
+	float simplifyTangentWeight;
+	float simplifyTangentSignWeight;
+} clodb200_builder_settings;
+/* GetDefaultBuilderSettings(), BasicRenderer/src/Import/DefaultCLodSettings.cpp:3-30 */
+clodb200_builder_settings clodb200_defaultBuilderSettings(void);
+
+/* MeshUvSetData (Import/MeshData.h:14-17): `count` float2 values; a set whose count differs from the vertex count reads
+ * as zeros, as the reference's (ClusterLODUtilities.cpp:1046). */
+typedef struct clodb200_uv_set
+{
+	const float* values;
+	size_t count;
+} clodb200_uv_set;
+
+/* The arguments of BuildClusterLODArtifactsFromGeometry as plain pointers. `vertices` is the interleaved stream of
+ * MeshVertexLayout (Mesh/VertexLayout.h: position f32x3 @0, normal f32x3 @12, uv f32x2 @24 if VERTEX_TEXCOORDS, then
+ * colour f32x3 if VERTEX_COLORS), vertex_flags the VertexFlags bits (Mesh/VertexFlags.h). `tangents` (float4 per vertex)
+ * replaces the reference's internal GenerateMikkTangents (:655-737) and is required when the stream has normals and
+ * texcoords and normal-attribute simplification is on; it may be NULL otherwise. Skinned meshes are not supported. */
+typedef struct clodb200_geometry
+{
+	const void* vertices;
+	size_t vertex_count;
+	unsigned int vertex_stride;
+	unsigned int vertex_flags;
+	const unsigned int* indices;
+	size_t index_count;
+	const clodb200_uv_set* uv_sets;
+	size_t uv_set_count;
+	const float* tangents;
+} clodb200_geometry;
+
+#define CLODB200_VERTEX_COLORS 1u
+#define CLODB200_VERTEX_NORMALS 2u
+#define CLODB200_VERTEX_TEXCOORDS 4u
+#define CLODB200_VERTEX_SKINNED 8u
+
+/* ClusterLODPrebuildArtifacts (ClusterLODTypes.h:165-169) as named arrays of the reference's PODs; see
+ * clodb200_artifactsGet. Empty / invalid geometry gives artifacts with empty arrays, as the reference does. */
+typedef struct clodb200_artifacts clodb200_artifacts;
+clodb200_artifacts* clodb200_buildArtifacts(const clodb200_geometry* geometry, const clodb200_builder_settings* settings);
+
+/* Geometry kept in HBM: upload once, build many times (benchmarks, scene batches). */
+typedef struct clodb200_device_geometry clodb200_device_geometry;
+clodb200_device_geometry* clodb200_geometryUpload(const clodb200_geometry* geometry, const clodb200_builder_settings* settings);
+void clodb200_geometryFree(clodb200_device_geometry* geometry);
+clodb200_artifacts* clodb200_geometryBuildArtifacts(const clodb200_device_geometry* geometry);
+
+/* Names: "groups" (ClusterLODGroup, 76 B), "segments" (ClusterLODGroupSegment, 16 B), "segmentBounds" (float4),
+ * "groupChunks" (ClusterLODGroupChunk, 20 B), "groupPageReferences" / "groupPageReferenceOffsets" (u32), "nodes"
+ * (ClusterLODNode, 64 B), "lodNodeRanges" ({u32 offset, u32 count}), "lodLevelRoots" (u32), "objectBoundingSphere"
+ * (float4), "counts" (u32 {trianglePageCount, voxelPageBase, voxelPageCount, maxDepth, maxTraversalDepth}),
+ * "meshPages" (cacheBuildData.meshPageBlobs back to back; pinned host memory), "meshPageOffsets" (u64[pages + 1]),
+ * "stats" (u64[16]: meshlets, groups, segments, pages, page bytes, meshlet-vertex refs, triangles over all levels,
+ * group-unique vertices, levels, simplified triangles, device-to-host bytes, nodes). Returns 1 if the name exists. */
+int clodb200_artifactsGet(const clodb200_artifacts* artifacts, const char* name, const void** out_ptr, size_t* out_bytes);
+void clodb200_artifactsFree(clodb200_artifacts* artifacts);
+
+/* CLod cache files (BasicRenderer/src/Import/CLodCache.cpp): writes `<directory>/<container_file_name>` — the .clodbin
+ * container (ContainerHeader + page directory + page blobs, :252-259, 314-375) — and `<directory>/<metadata_file_name>`,
+ * the bytes of SerializeMetadata (:169-207) that the reference stores as `uchar[] clodBlob` on prim /CLodCache of its
+ * .usdc stage (:528-574; the OpenUSD crate wrapper itself is not written here). The file names are
+ * the caller's: the reference derives them with boost::hash_combine (:586-633), which is not restated. */
+int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char* directory, const char* container_file_name, const char* metadata_file_name,
+    const char* source_identifier, const char* prim_path, const char* subset_name, uint64_t build_config_hash);
+/* The metadata blob alone: returns the byte count; writes at most `capacity` bytes. */
+size_t clodb200_artifactsSerializeMetadata(const clodb200_artifacts* artifacts, const char* container_file_name, const char* source_identifier, const char* prim_path,
+    const char* subset_name, uint64_t build_config_hash, void* buffer, size_t capacity);
 
 /* CUDA-event stopwatch on the build stream: Start records an event, Stop records another, synchronises and returns the
  * elapsed device time in milliseconds (bench.py brackets its timed steps with these). */

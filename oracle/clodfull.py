@@ -60,6 +60,19 @@ def _lib(ours: bool):
     return _libs[ours]
 
 
+def last_attributes() -> np.ndarray:
+    """[V, A] simplification attribute stream the reference builder handed to clodBuildEx in the last build(..., clodb200_lib=...)
+    call (normals, then its MikkTSpace tangents xyz + sign when the mesh has UVs)."""
+    lib = _lib(True)
+    lib.clodshim_last_attributes.restype = C.c_void_p
+    lib.clodshim_last_attributes.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    v, a = C.c_size_t(), C.c_size_t()
+    ptr = lib.clodshim_last_attributes(C.byref(v), C.byref(a))
+    if not v.value or not a.value:
+        return np.zeros((0, 0), np.float32)
+    return np.frombuffer((C.c_float * (v.value * a.value)).from_address(ptr), np.float32).reshape(v.value, a.value).copy()
+
+
 class Artifacts:
     def __init__(self, arrays, seconds):
         self.__dict__.update(arrays)

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <vector>
 
 namespace
 {
@@ -55,8 +56,25 @@ Clodb& lib()
 static_assert(sizeof(clodConfig) == sizeof(clodb200_config) && sizeof(clodMesh) == sizeof(clodb200_mesh) && sizeof(clodCluster) == sizeof(clodb200_cluster) && sizeof(clodGroup) == sizeof(clodb200_group),
     "clodb200 structs must be layout-identical to the reference's");
 
+// The simplification attribute stream of the last build (normals + the reference's MikkTSpace tangents): test input for
+// clodb200_buildArtifacts, whose caller supplies the tangents the reference generates internally.
+static std::vector<float> g_last_attributes;
+static size_t g_last_attribute_count = 0;
+
+extern "C" const float* clodshim_last_attributes(size_t* vertex_count, size_t* attribute_count)
+{
+	*attribute_count = g_last_attribute_count;
+	*vertex_count = g_last_attribute_count ? g_last_attributes.size() / g_last_attribute_count : 0;
+	return g_last_attributes.data();
+}
+
 extern "C" size_t clodBuildEx(clodConfig config, clodMesh mesh, void* output_context, clodOutputEx output_callback, const clodBuildParallelConfig*)
 {
+	g_last_attribute_count = mesh.vertex_attributes ? mesh.attribute_count : 0;
+	g_last_attributes.clear();
+	for (size_t i = 0; i < mesh.vertex_count && g_last_attribute_count; ++i)
+		g_last_attributes.insert(g_last_attributes.end(), mesh.vertex_attributes + i * (mesh.vertex_attributes_stride / sizeof(float)),
+		    mesh.vertex_attributes + i * (mesh.vertex_attributes_stride / sizeof(float)) + g_last_attribute_count);
 	clodb200_config cfg;
 	memcpy(&cfg, &config, sizeof(cfg));
 	clodb200_mesh m;

@@ -14,10 +14,12 @@ warm = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 lib = load(0)
 m = meshgen.grid(n, seed=1234)
-h = lib.upload_mesh(m.positions, m.indices, attributes=m.normals, attribute_weights=np.ones(3, np.float32), protect_mask=7)
+from basicrenderer_b200 import artifacts as art  # noqa: E402
+
+h = lib.upload_geometry(art.interleave(m.positions, m.normals), m.indices, art.VERTEX_NORMALS)
 for it in range(warm + steps):
     l0 = lib.launch_count
     t = time.time()
-    rec = lib.build_dag_resident(h, keep_indices=False)
-    print(f"build {it}: {time.time() - t:.3f} s, launches {lib.launch_count - l0}", flush=True)
-lib.free_mesh(h)
+    rec = lib.build_artifacts_resident(h, views=True)
+    print(f"build {it}: {time.time() - t:.3f} s, launches {lib.launch_count - l0}, pages {rec.stat['pages']}", flush=True)
+lib.free_geometry(h)
