@@ -204,7 +204,8 @@ DEVFN u32 vertex_hash(u32 v)
 
 // (group, vertex) set shared by all meshlets: the number of first insertions per group is ClusterLODGroup::groupVertexCount
 // (distinct vertices of the group, CLU.cpp:886-901, 984)
-DEVFN void group_vertex_insert(u64* table, u64 mask, u32 group, u32 v, u32* group_vertex_count)
+// returns true when this call inserted the pair (exactly one caller per distinct pair sees true)
+DEVFN bool group_vertex_insert(u64* table, u64 mask, u32 group, u32 v)
 {
 	u64 key = (u64(group) << 32) | v;
 	u64 h = (key * 0x9E3779B97F4A7C15ull) >> 20;
@@ -213,12 +214,9 @@ DEVFN void group_vertex_insert(u64* table, u64 mask, u32 group, u32 v, u32* grou
 		h &= mask;
 		unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&table[h]), ~0ull, (unsigned long long)key);
 		if (old == ~0ull)
-		{
-			atomicAdd(&group_vertex_count[group], 1u);
-			return;
-		}
+			return true;
 		if (old == key)
-			return;
+			return false;
 		h++;
 	}
 }
@@ -276,8 +274,11 @@ KERNEL k_meshlet_prepass(const MeshletJob* __restrict__ jobs, u32 M, LevelTable 
 		atomicOr(errors, 1u);
 		return;
 	}
+	u32 inserted = 0;
 	for (u32 vi = 0; vi < count; ++vi)
-		group_vertex_insert(table, table_mask, job.group, t.vertices[vi], group_vertex_count);
+		inserted += group_vertex_insert(table, table_mask, job.group, t.vertices[vi]) ? 1u : 0u;
+	if (inserted)
+		atomicAdd(&group_vertex_count[job.group], inserted);
 	for (u32 s = 0; s < vs.uv_set_count; ++s)
 	{
 		float mn_u = FLT_MAX, mn_v = FLT_MAX, mx_u = -FLT_MAX, mx_v = -FLT_MAX;
@@ -472,8 +473,15 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_meshlet_prepass_warp(c
 			atomicOr(errors, 1u);
 		return;
 	}
+	// one counter update per meshlet: every lane's first insertions are summed across the warp first (the group counter is
+	// shared by up to 512 meshlets x 128 vertices, per-vertex atomics on it serialise)
+	u32 inserted = 0;
 	for (u32 vi = lane; vi < count; vi += 32)
-		group_vertex_insert(table, table_mask, job.group, t.vertices[vi], group_vertex_count);
+		inserted += group_vertex_insert(table, table_mask, job.group, t.vertices[vi]) ? 1u : 0u;
+	for (int o = 16; o > 0; o >>= 1)
+		inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
+	if (lane == 0 && inserted)
+		atomicAdd(&group_vertex_count[job.group], inserted);
 	for (u32 s = 0; s < vs.uv_set_count; ++s)
 	{
 		float mn_u = FLT_MAX, mn_v = FLT_MAX, mx_u = -FLT_MAX, mx_v = -FLT_MAX;

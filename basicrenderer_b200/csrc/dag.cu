@@ -8,6 +8,7 @@
 
 #include <cfloat>
 #include <algorithm>
+#include <chrono>
 
 namespace clodb
 {
@@ -135,9 +136,41 @@ static size_t emit_level(const ClusterSet& cs, const LevelHost& host, const std:
 	return cs.cluster_count;
 }
 
+// CLODB200_LEVEL_TIMES=1: host wall time per stage and level on stderr (each mark synchronises the build stream, so the
+// sum is slower than an untraced build; diagnostics only)
+struct StageClock
+{
+	bool on;
+	std::chrono::steady_clock::time_point t0;
+	StageClock()
+	    : on(getenv("CLODB200_LEVEL_TIMES") != nullptr)
+	{
+		restart();
+	}
+	void restart()
+	{
+		if (on)
+		{
+			dev_sync();
+			t0 = std::chrono::steady_clock::now();
+		}
+	}
+	double lap()
+	{
+		if (!on)
+			return 0;
+		dev_sync();
+		auto t1 = std::chrono::steady_clock::now();
+		double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+		t0 = t1;
+		return ms;
+	}
+};
+
 size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indices_dev, size_t index_count, Workspace& ws, DagSink& sink, BuildStats& stats)
 {
 	stats = BuildStats();
+	StageClock clock;
 	u32 T0 = u32(index_count / 3);
 	size_t V = mesh.vertex_count;
 	Arena& persist = ws.persist;
@@ -164,6 +197,8 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 
 	std::vector<int> refined_host(level.cluster_count, -1);
 	int depth = 0;
+	if (clock.on)
+		fprintf(stderr, "level -1: remap + first clusterize + bounds %.3f ms (T %u K %u)\n", clock.lap(), T0, level.cluster_count);
 
 	while (level.cluster_count > 1)
 	{
@@ -175,6 +210,8 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		GroupSet groups = partition_clusters(level.tri, level.cluster_tri_offset, K, refined_dev, bounds5, remap, mesh.positions, V, config, ws);
 		u32 G = groups.group_count;
 		stats.level_groups.push_back(G);
+		double t_partition = clock.lap();
+		u64 launches0 = g_launches;
 
 		ArenaScope level_scope(temp);
 		u32* gtri = temp.alloc<u32>(size_t(level.triangle_count) * 3);
@@ -189,7 +226,9 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		float* group_bounds5_dev = temp.alloc<float>(size_t(G) * 5);
 		group_bounds_merge(bounds5, groups.group_cluster_offset, groups.group_clusters, G, group_bounds5_dev);
 
+		double t_locks = clock.lap();
 		SimplifyOutput simp = simplify_groups(gtri, group_tri_offset_host.data(), G, mesh, remap, locks, config, ws);
+		double t_simplify = clock.lap();
 		stats.simplify_passes += g_simplify_stats.passes;
 		stats.simplify_rounds += g_simplify_stats.rounds;
 
@@ -233,6 +272,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 
 		std::vector<int> group_ids;
 		emit_level(level, level_host, refined_host, bounds5_host, precise4, config, groups, group_clusters_host, group_bounds5, depth, sink, group_ids, stats);
+		double t_emit = clock.lap();
 
 		// segments for re-clusterization: simplified lists of non-terminal groups
 		std::vector<u32> seg_src, seg_dst(1, 0);
@@ -285,6 +325,9 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 			LAUNCH(k_assign_cluster_parent, next.cluster_count, next.cluster_segment, d_ref, d_b5, refined_dev, bounds5, next.cluster_count);
 		}
 		refined_host = dev_download(refined_dev, next.cluster_count);
+		if (clock.on)
+			fprintf(stderr, "level %d: T %u K %u G %u | partition %.3f locks %.3f simplify %.3f (passes %u sloppy %u) emit %.3f clusterize %.3f ms | launches %llu\n", depth - 1, level.triangle_count, K, G,
+			    t_partition, t_locks, t_simplify, g_simplify_stats.passes, g_simplify_stats.sloppy_groups, t_emit, clock.lap(), (unsigned long long)(g_launches - launches0));
 		level = next;
 	}
 
