@@ -295,3 +295,136 @@ def scene_mesh(i: int, target_tris: float) -> Mesh:
     nu = max(3, int(round((target_tris / 2.0 * 2.0) ** 0.5)))
     nv = max(3, int(round(target_tris / 2.0 / nu)))
     return torus(nu, nv, seed=i)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config C3 at full size (f = 2236: 99 993 920 triangles, 50 M wedges). The numpy generator above needs minutes and tens of
+# GB of float64 temporaries at that size; this is the same construction written with torch ops so that it can run on the
+# GPU that is about to build the mesh. Deterministic; on CPU it reproduces icosphere(f, True, True) (tests/test_meshgen.py).
+
+
+def _t_hash_u32(x):
+    m = 0xFFFFFFFF
+    x = x & m
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & m
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & m
+    x = x ^ (x >> 16)
+    return x
+
+
+def _t_lattice(ix, iy, iz, seed):
+    m = 0xFFFFFFFF
+    h = _t_hash_u32((((ix & m) * 0x9E3779B1) & m) ^ _t_hash_u32((((iy & m) * 0x85EBCA77) & m) ^ _t_hash_u32((((iz & m) * 0xC2B2AE3D) & m) ^ (seed & m))))
+    return (h >> 8).double() * (1.0 / 16777216.0) * 2.0 - 1.0
+
+
+def _t_value_noise3(p, seed):
+    import torch
+
+    pf = torch.floor(p)
+    t = p - pf
+    t = t * t * (3.0 - 2.0 * t)
+    i = pf.long()
+    ix, iy, iz = i[:, 0], i[:, 1], i[:, 2]
+    out = torch.zeros(p.shape[0], dtype=torch.float64, device=p.device)
+    for dx in (0, 1):
+        wx = t[:, 0] if dx else 1.0 - t[:, 0]
+        for dy in (0, 1):
+            wy = t[:, 1] if dy else 1.0 - t[:, 1]
+            for dz in (0, 1):
+                wz = t[:, 2] if dz else 1.0 - t[:, 2]
+                out += wx * wy * wz * _t_lattice(ix + dx, iy + dy, iz + dz, seed)
+    return out
+
+
+def icosphere_seams_torch(f: int, seed: int = 42, device=None, chunk: int = 1 << 23):
+    """icosphere(f, displace=True, uv_atlas=True) built with torch on `device` (default: cuda if available).
+
+    Returns (Mesh, tangents[V,4] f32). The tangent stream is analytic — the chart's dP/du projected onto the tangent plane
+    of the vertex normal, w = +1 — and differs across chart borders like the UVs do; it stands in for the MikkTSpace
+    stream the reference generates internally (clodb200_geometry::tangents, include/clodb200.h)."""
+    import torch
+
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    f64 = torch.float64
+    ar = torch.arange(f + 1, device=dev)
+    ii = ar.view(-1, 1).expand(f + 1, f + 1)
+    jj = ar.view(1, -1).expand(f + 1, f + 1)
+    keep = (ii + jj) <= f
+    bi, bj = ii[keep], jj[keep]
+    npf = bi.numel()
+    lid = torch.full((f + 1, f + 1), -1, dtype=torch.int64, device=dev)
+    lid[bi, bj] = torch.arange(npf, device=dev)
+    af = torch.arange(f, device=dev)
+    ui = af.view(-1, 1).expand(f, f)
+    uj = af.view(1, -1).expand(f, f)
+    um = (ui + uj) < f
+    ui_, uj_ = ui[um], uj[um]
+    up = torch.stack([lid[ui_, uj_], lid[ui_ + 1, uj_], lid[ui_, uj_ + 1]], dim=1)
+    dm = (ui + uj) < f - 1
+    di, dj = ui[dm], uj[dm]
+    down = torch.stack([lid[di + 1, dj], lid[di + 1, dj + 1], lid[di, dj + 1]], dim=1)
+    ltris = torch.cat([up, down], dim=0)
+    del lid, up, down, ui_, uj_, di, dj
+    bk = f - bi - bj
+    w = torch.stack([bk, bi, bj], dim=1).to(f64) / f
+    icov = torch.tensor(_ICO_V, dtype=f64, device=dev)
+
+    V = npf * 20
+    verts = torch.empty((V, 8), dtype=torch.float32, device=dev)
+    tang = torch.empty((V, 4), dtype=torch.float32, device=dev)
+    qk = torch.empty(V, dtype=torch.int64, device=dev)
+
+    def radius(d):
+        return 1.0 + 0.02 * _t_value_noise3(d * 8.0 + 100.0, seed) + 0.002 * _t_value_noise3(d * 64.0 + 100.0, seed + 1)
+
+    def dirn(v):
+        return v / torch.linalg.norm(v, dim=1, keepdim=True)
+
+    ex = torch.tensor([[1.0, 0.0, 0.0]], dtype=f64, device=dev)
+    ey = torch.tensor([[0.0, 1.0, 0.0]], dtype=f64, device=dev)
+    eps = 1e-3
+    for fi, (a, b, c) in enumerate(_ICO_F):
+        for s in range(0, npf, chunk):
+            e = min(npf, s + chunk)
+            ws = w[s:e]
+            P = ws[:, 0:1] * icov[a] + ws[:, 1:2] * icov[b] + ws[:, 2:3] * icov[c]
+            P = P / torch.linalg.norm(P, dim=1, keepdim=True)
+            r = radius(P)
+            ref = torch.where(P[:, 0:1].abs() < 0.9, ex, ey)
+            t1 = torch.linalg.cross(P, ref.expand_as(P))
+            t1 = t1 / torch.linalg.norm(t1, dim=1, keepdim=True)
+            t2 = torch.linalg.cross(P, t1)
+            g1 = (radius(dirn(P + eps * t1)) - radius(dirn(P - eps * t1))) / (2 * eps)
+            g2 = (radius(dirn(P + eps * t2)) - radius(dirn(P - eps * t2))) / (2 * eps)
+            N = P * r[:, None] - t1 * g1[:, None] - t2 * g2[:, None]
+            N = N / torch.linalg.norm(N, dim=1, keepdim=True)
+            Pd = P * r[:, None]
+            o = fi * npf
+            verts[o + s : o + e, 0:3] = Pd.float()
+            verts[o + s : o + e, 3:6] = N.float()
+            cx, cy = (fi % 5) * 0.2, (fi // 5) * 0.25
+            verts[o + s : o + e, 6] = (cx + 0.01 + 0.18 * (ws[:, 1] + 0.5 * ws[:, 2])).float()
+            verts[o + s : o + e, 7] = (cy + 0.01 + 0.23 * ws[:, 2]).float()
+            q = torch.round(Pd / torch.linalg.norm(Pd, dim=1, keepdim=True) * (4.0 * f)).long()
+            qk[o + s : o + e] = (q[:, 0] + (1 << 20)) | ((q[:, 1] + (1 << 20)) << 21) | ((q[:, 2] + (1 << 20)) << 42)
+            # chart u direction (towards corner b), made tangent to the shaded surface
+            du = (icov[b] - icov[a]).view(1, 3)
+            T = du - N * (N * du).sum(dim=1, keepdim=True)
+            T = T / torch.linalg.norm(T, dim=1, keepdim=True)
+            tang[o + s : o + e, 0:3] = T.float()
+            tang[o + s : o + e, 3] = 1.0
+            del P, r, t1, t2, g1, g2, N, Pd, q, T
+    # chart borders must carry bit-identical positions/normals so that they weld by position (seams, not cracks)
+    _, inverse = torch.unique(qk, return_inverse=True)
+    first = torch.full((int(inverse.max()) + 1,), V, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, inverse, torch.arange(V, device=dev), reduce="amin")
+    src = first[inverse]
+    del qk, inverse, first
+    verts[:, 0:6] = verts[src, 0:6]
+    del src
+    tris = torch.cat([ltris + fi * npf for fi in range(20)], dim=0).reshape(-1).to(torch.int32)
+    mesh = Mesh(verts.cpu().numpy(), tris.cpu().numpy().view(np.uint32), VERTEX_NORMALS | VERTEX_TEXCOORDS, f"icosphere{f}_disp_uv")
+    return mesh, tang.cpu().numpy()

@@ -105,12 +105,24 @@ def _dist():
     return rank, world, local
 
 
+WORKLOAD = os.environ.get("CLODB200_BENCH_WORKLOAD", "C2").upper()  # "C3": the 100 M-triangle seamed icosphere (opt-in, N = 1)
+C3_F = 2236  # icosphere frequency => 99 993 920 triangles
+
+
 def _workload(rank: int, world: int):
     """N = 1: the C2 heightfield. N > 1: mesh `rank` of a batch of equally sized heightfields with distinct noise seeds
-    (weak scaling: per-GPU work is fixed; meshes are independent, the C4 sharding rule)."""
+    (weak scaling: per-GPU work is fixed; meshes are independent, the C4 sharding rule).
+    Returns (mesh, tangents or None)."""
+    if WORKLOAD == "C3":
+        f = int(os.environ.get("CLODB200_BENCH_ICO_F", C3_F))
+        mesh, tangents = meshgen.icosphere_seams_torch(f, seed=42 + rank)
+        import torch
+
+        torch.cuda.empty_cache()
+        return mesh, tangents
     seed = 1234 if world == 1 else 1234 + rank
     n = int(os.environ.get("CLODB200_BENCH_GRID", WORKLOAD_N))
-    return meshgen.grid(n, seed=seed)
+    return meshgen.grid(n, seed=seed), None
 
 
 def _pin(a: np.ndarray) -> np.ndarray:
@@ -136,13 +148,18 @@ def run_ours(args):
     from basicrenderer_b200 import load, sharding
 
     lib = load(local)
-    mesh = _workload(rank, world)
+    mesh, tangents = _workload(rank, world)
     T = mesh.triangle_count
     from basicrenderer_b200 import artifacts as art
 
-    vertices = _pin(art.interleave(mesh.positions, mesh.normals))
+    if tangents is None:
+        vertices = _pin(art.interleave(mesh.positions, mesh.normals))
+        flags = art.VERTEX_NORMALS
+    else:
+        vertices = _pin(mesh.vertices)  # pos + normal + uv, 32-byte stride
+        tangents = _pin(tangents)
+        flags = art.VERTEX_NORMALS | art.VERTEX_TEXCOORDS
     indices = _pin(mesh.indices)
-    flags = art.VERTEX_NORMALS
 
     def barrier():
         if world > 1:
@@ -150,7 +167,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- resident-input timing (value)
-    handle = lib.upload_geometry(vertices, indices, flags)
+    handle = lib.upload_geometry(vertices, indices, flags, tangents=tangents)
     for _ in range(args.warmup):
         rec = lib.build_artifacts_resident(handle, views=True)
     stop = threading.Event()
@@ -177,14 +194,14 @@ def run_ours(args):
 
     # ---- end to end through the host-pointer C ABI (upload + build + page read-back every step)
     for _ in range(min(args.warmup, 2)):
-        lib.build_artifacts(vertices, indices, flags, views=True)
+        lib.build_artifacts(vertices, indices, flags, tangents=tangents, views=True)
     barrier()
     lib.timer_start()
     for _ in range(args.steps):
-        rec_e2e = lib.build_artifacts(vertices, indices, flags, views=True)
+        rec_e2e = lib.build_artifacts(vertices, indices, flags, tangents=tangents, views=True)
     ms_e2e = lib.timer_stop_ms()
     barrier()
-    h2d = vertices.nbytes + indices.nbytes
+    h2d = vertices.nbytes + indices.nbytes + (tangents.nbytes if tangents is not None else 0)
     d2h = int(rec_e2e.stat["d2h_bytes"])
 
     # ---- max over ranks
@@ -254,7 +271,10 @@ def run_ours(args):
             "dtype": "f32+u32",
             "data": "synthetic",
             "config": {
-                "workload": f"C2: {T}-triangle displaced heightfield grid (n={int(round((T / 2) ** 0.5))}), pos+normal, full DAG to a single root cluster" + ("" if world == 1 else f"; one such mesh per GPU ({world} independent meshes, sharded by mesh)"),
+                "workload": (f"C2: {T}-triangle displaced heightfield grid (n={int(round((T / 2) ** 0.5))}), pos+normal, full DAG to a single root cluster" if WORKLOAD != "C3" else
+                             f"C3: {T}-triangle noisy displaced icosphere (f={int(round((T / 20) ** 0.5))}) with normals + per-face UV atlas seams, 7 simplification attributes (normal + tangent xyz + sign), "
+                             "full DAG to a single root cluster; tangent stream supplied by the caller (analytic), the reference generates MikkTSpace tangents inside its call")
+                            + ("" if world == 1 else f"; one such mesh per GPU ({world} independent meshes, sharded by mesh)"),
                 "builder": "clodDefaultConfig(128) + BasicRenderer overrides (128/128/64, partition 384, 8 refined ids, spatial clusters)",
                 "l2": "inputs and per-level working sets (>= 240 MB) exceed the 126 MB L2; no explicit flush",
                 "levels": rec.stat["levels"],
@@ -264,7 +284,7 @@ def run_ours(args):
                 "pages": rec.stat["pages"],
                 "page_bytes": rec.stat["page_bytes"],
                 "scope": "BuildClusterLODArtifactsFromGeometry, mesh mode: remap, clusterize, partition, lock, simplify, bounds, error rule, group tables, traversal hierarchy, mesh page packing, page blobs read back to host",
-                "whole_job_roofline": _whole_job_roofline(rec.stat, T, ms / args.steps, peak),
+                "whole_job_roofline": _whole_job_roofline(rec.stat, T, ms / args.steps, peak, 24 if WORKLOAD != "C3" else 48),
             },
             "clocks": _clock_summary(clock_samples),
             "e2e": {"value": e2e_value, "unit": "Mtris/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
@@ -280,16 +300,18 @@ def run_ours(args):
         print(json.dumps(result))
 
 
-def _whole_job_roofline(stat, T0, ms_per_step, peak_gbs):
+def _whole_job_roofline(stat, T0, ms_per_step, peak_gbs, s_v=24):
     """compulsory bytes of the whole build from the builder's own output sums,
-    B = 24*sum T_l + S_v*sum V_l + 12*sum T_{l+1} + page bytes (S_v = 24 B for pos+normal)."""
-    b = 24 * stat["level_triangles"] + 24 * stat["group_vertices"] + 12 * stat["simplified_triangles"] + stat["page_bytes"]
+    B = 24*sum T_l + S_v*sum V_l + 12*sum T_{l+1} + page bytes (S_v = 24 B for pos+normal, 48 B with uv + tangent4)."""
+    b = 24 * stat["level_triangles"] + s_v * stat["group_vertices"] + 12 * stat["simplified_triangles"] + stat["page_bytes"]
     gbs = b / (ms_per_step * 1e-3) / 1e9
     return {"algorithmic_bytes": int(b), "bytes_per_input_triangle": b / T0, "achieved_gbs": gbs, "frac": gbs / peak_gbs}
 
 
 def _reference_sample_mesh():
     # bounded sample of the workload: a 1 M-triangle tile of the same heightfield generator and density
+    if WORKLOAD == "C3":
+        return meshgen.icosphere(int(os.environ.get("CLODB200_REF_ICO_F", 224)), True, True)
     n = int(os.environ.get("CLODB200_REF_GRID", 707))
     return meshgen.grid(n, seed=1234)
 
@@ -299,11 +321,16 @@ def _reference_build(m, threads):
     BuildClusterLODArtifactsFromGeometry with its own clodBuildEx, mesh mode) on host arrays; returns seconds inside the call."""
     from oracle import clodfull
 
+    if WORKLOAD == "C3":
+        return clodfull.build(m.vertices, m.indices, flags=m.flags, threads=threads).seconds
     v = clodfull.interleave(m.positions, m.normals)
     return clodfull.build(v, m.indices, flags=clodfull.VERTEX_NORMALS, threads=threads).seconds
 
 
 def _reference_sample_text(m, threads, dt):
+    if WORKLOAD == "C3":
+        return (f"{m.triangle_count}-triangle icosphere of the C3 generator (f=224, same displacement, normals and UV atlas seams), unmodified "
+                f"BuildClusterLODArtifactsFromGeometry in mesh mode incl. its MikkTSpace tangent generation, std::thread pool of {threads} in place of oneTBB, {dt:.2f} s per build")
     return (f"{m.triangle_count}-triangle tile of the C2 heightfield (same generator/density; the reference is ~80 % serial, so Mtris/s is size "
             f"independent to first order), unmodified BuildClusterLODArtifactsFromGeometry in mesh mode (meshoptimizer v1.0 + clusterlod.h + L3 builder, "
             f"std::thread pool of {threads} in place of oneTBB), {dt:.2f} s per build; includes the reference's unused VoxelSourceTriangleBVH::Build (SURVEY.md §8a a20)")
@@ -322,7 +349,7 @@ def cpu_baseline_sample():
         out = {"value": m.triangle_count / dt / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "reference", "sample": _reference_sample_text(m, threads, dt)}
         if clodref.available():
             t0 = time.perf_counter()
-            clodref.dag_build_timed(m.positions, m.indices, m.normals, ATTR_WEIGHTS, PROTECT_MASK, threads=threads)
+            clodref.dag_build_timed(np.ascontiguousarray(m.positions), m.indices, np.ascontiguousarray(m.normals), ATTR_WEIGHTS, PROTECT_MASK, threads=threads)
             out["clodBuildEx_only_mtris_s"] = m.triangle_count / (time.perf_counter() - t0) / 1e6
         return out
     except Exception as e:  # pragma: no cover
@@ -357,7 +384,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32+u32",
         "data": "synthetic",
-        "config": {"workload": "C2 heightfield, reference BuildClusterLODArtifactsFromGeometry (mesh mode) on host cores", "sample": sample},
+        "config": {"workload": f"{WORKLOAD if WORKLOAD == 'C3' else 'C2'} workload, reference BuildClusterLODArtifactsFromGeometry (mesh mode) on host cores", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -371,10 +398,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # exactly one line on stdout: libraries that write to fd 1 (NCCL's version banner) are sent to stderr for the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
