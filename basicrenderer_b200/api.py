@@ -122,6 +122,9 @@ class ClodLib:
         L.clodb200_lockBoundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
         L.clodb200_simplifyGroups.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.clodb200_simplifyStats.argtypes = [C.c_void_p]
+        L.clodb200_primExclusiveScanU32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        L.clodb200_primExclusiveMaxScanU64.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+        L.clodb200_primSortPairsU32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.clodb200_buildRecorded.restype = C.c_void_p
         L.clodb200_buildRecorded.argtypes = [Config, MeshDesc]
         L.clodb200_meshUpload.restype = C.c_void_p
@@ -148,6 +151,29 @@ class ClodLib:
 
     def builder_config(self) -> Config:
         return self._lib.clodb200_builderConfig()
+
+    # ---- device-wide primitives (parity tests / micro-benchmarks); each returns (result..., mean ms of the timed runs)
+    def prim_exclusive_scan_u32(self, values: np.ndarray, repeat: int = 1):
+        values = np.ascontiguousarray(values, dtype=np.uint32)
+        out = np.empty_like(values)
+        total = np.zeros(1, np.uint32)
+        ms = C.c_float(0)
+        self._check(self._lib.clodb200_primExclusiveScanU32(_ptr(values), _ptr(out), values.size, _ptr(total), repeat, C.byref(ms)))
+        return out, int(total[0]), ms.value
+
+    def prim_exclusive_max_scan_u64(self, values: np.ndarray, repeat: int = 1):
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        out = np.empty_like(values)
+        ms = C.c_float(0)
+        self._check(self._lib.clodb200_primExclusiveMaxScanU64(_ptr(values), _ptr(out), values.size, repeat, C.byref(ms)))
+        return out, ms.value
+
+    def prim_sort_pairs_u32(self, keys: np.ndarray, values: np.ndarray, bit_lo: int = 0, bit_hi: int = 32, repeat: int = 1):
+        keys = np.array(keys, dtype=np.uint32)
+        values = np.array(values, dtype=np.uint32)
+        ms = C.c_float(0)
+        self._check(self._lib.clodb200_primSortPairsU32(_ptr(keys), _ptr(values), keys.size, bit_lo, bit_hi, repeat, C.byref(ms)))
+        return keys, values, ms.value
 
     def position_remap(self, positions: np.ndarray, stride: int | None = None, vertex_count: int | None = None) -> np.ndarray:
         if stride is None:

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include <mutex>
+#include <functional>
 
 using namespace clodb;
 
@@ -1217,6 +1218,103 @@ size_t clodb200_profileReport(char* buffer, size_t capacity)
 		buffer[n] = 0;
 	}
 	return report.size() + 1;
+}
+
+// ---- device-wide primitives, exposed for their own parity tests and micro-benchmarks (tests/test_prims.py) ------------
+// Each call uploads the input, runs the primitive `repeat` times on the build stream (first run untimed when repeat > 1),
+// downloads the result of the last run and returns the mean device time of the timed runs in *ms (may be NULL).
+static float timed_runs(int repeat, const std::function<void()>& run)
+{
+	float ms = 0.f;
+	run();
+#ifndef CLODB_EMU
+	if (repeat > 1)
+	{
+		cudaEvent_t a, b;
+		cudaEventCreate(&a);
+		cudaEventCreate(&b);
+		cudaEventRecord(a, g_stream);
+		for (int i = 1; i < repeat; ++i)
+			run();
+		cudaEventRecord(b, g_stream);
+		cudaEventSynchronize(b);
+		cudaEventElapsedTime(&ms, a, b);
+		ms /= float(repeat - 1);
+		cudaEventDestroy(a);
+		cudaEventDestroy(b);
+	}
+#else
+	for (int i = 1; i < repeat; ++i)
+		run();
+#endif
+	return ms;
+}
+
+int clodb200_primExclusiveScanU32(const unsigned int* in, unsigned int* out, size_t n, unsigned int* total, int repeat, float* ms)
+{
+	return guarded([&]() -> int {
+		if (n && (!in || !out))
+			return fail(CLODB200_ERR_INVALID, "clodb200_primExclusiveScanU32: invalid arguments");
+		ensure_workspace(n * 8 + (1 << 20), 1 << 20);
+		u32* din = g_ws.persist.alloc<u32>(n + 1);
+		u32* dout = g_ws.persist.alloc<u32>(n + 1);
+		u32* dtotal = g_ws.persist.alloc<u32>(4);
+		dev_h2d(din, in, n * sizeof(u32));
+		float t = timed_runs(repeat, [&]() { exclusive_scan_u32(din, dout, n, dtotal, g_ws.temp); });
+		dev_d2h(out, dout, n * sizeof(u32));
+		if (total)
+			dev_d2h(total, dtotal, sizeof(u32));
+		if (ms)
+			*ms = t;
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_primExclusiveMaxScanU64(const uint64_t* in, uint64_t* out, size_t n, int repeat, float* ms)
+{
+	return guarded([&]() -> int {
+		if (n && (!in || !out))
+			return fail(CLODB200_ERR_INVALID, "clodb200_primExclusiveMaxScanU64: invalid arguments");
+		ensure_workspace(n * 16 + (1 << 20), 1 << 20);
+		u64* din = g_ws.persist.alloc<u64>(n + 1);
+		u64* dout = g_ws.persist.alloc<u64>(n + 1);
+		dev_h2d(din, in, n * sizeof(u64));
+		float t = timed_runs(repeat, [&]() { exclusive_scan<u64, OpMaxU64>(din, dout, n, nullptr, g_ws.temp); });
+		dev_d2h(out, dout, n * sizeof(u64));
+		if (ms)
+			*ms = t;
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_primSortPairsU32(unsigned int* keys, unsigned int* values, size_t n, int bit_lo, int bit_hi, int repeat, float* ms)
+{
+	return guarded([&]() -> int {
+		if (n && (!keys || !values))
+			return fail(CLODB200_ERR_INVALID, "clodb200_primSortPairsU32: invalid arguments");
+		if (bit_lo < 0 || bit_hi > 32 || bit_hi < bit_lo)
+			return fail(CLODB200_ERR_INVALID, "clodb200_primSortPairsU32: invalid bit range");
+		ensure_workspace(n * 24 + (1 << 20), n * 8 + (16 << 20));
+		u32* k0 = g_ws.persist.alloc<u32>(n + 1);
+		u32* v0 = g_ws.persist.alloc<u32>(n + 1);
+		u32* k = g_ws.persist.alloc<u32>(n + 1);
+		u32* v = g_ws.persist.alloc<u32>(n + 1);
+		u32* kt = g_ws.persist.alloc<u32>(n + 1);
+		u32* vt = g_ws.persist.alloc<u32>(n + 1);
+		dev_h2d(k0, keys, n * sizeof(u32));
+		dev_h2d(v0, values, n * sizeof(u32));
+		// the copies that restore the unsorted input are part of every run (and of the reported time)
+		float t = timed_runs(repeat, [&]() {
+			dev_d2d(k, k0, n * sizeof(u32));
+			dev_d2d(v, v0, n * sizeof(u32));
+			radix_sort_pairs<u32>(k, kt, v, vt, n, bit_lo, bit_hi, g_ws.temp);
+		});
+		dev_d2h(keys, k, n * sizeof(u32));
+		dev_d2h(values, v, n * sizeof(u32));
+		if (ms)
+			*ms = t;
+		return CLODB200_OK;
+	});
 }
 
 void clodb200_simplifyStats(unsigned int out3[3])

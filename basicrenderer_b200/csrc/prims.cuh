@@ -184,6 +184,7 @@ struct ScanChain
 	u32* flags = nullptr;    // per tile: (epoch << 2) | {1 = aggregate ready, 2 = inclusive prefix ready}
 	char* aggregate = nullptr; // SCAN_CHAIN_VALUE_BYTES per tile
 	char* inclusive = nullptr;
+	char* desc = nullptr; // packed {status, value} descriptors of the 4-/8-byte scans, 16 bytes per tile
 	size_t capacity_tiles = 0;
 	u32 epoch = 0;
 };
@@ -327,37 +328,190 @@ DEVFN T scan_chain_lookback(u32 tile, const T& tile_aggregate, u32* flags, char*
 	return prefix;
 }
 
+// ---- packed descriptors for 4- and 8-byte values ---------------------------------------------------------------------
+// A look-back iteration costs one L2 round trip (~0.7 us on B200) and resolves one window of predecessors, so the chain
+// advances at most window / round-trip tiles per second. With separate flag and value arrays (two dependent round trips and
+// a fence per window of 32) that bound is ~20 tiles/us = 0.3 TB/s of 8 KB tiles. Here status and value share one word that
+// is written and read with a single aligned access (no fence, one round trip), every lane inspects SCAN_LOOK descriptors per
+// iteration (window = 32 * SCAN_LOOK tiles), and large inputs use 32 KB tiles: the bound moves above the HBM rate.
+static const int SCAN_LOOK = 4;
+
+template <typename T>
+struct ScanDesc;
+
+template <>
+struct ScanDesc<u32>
+{
+	typedef unsigned long long Word;
+	DEVFN Word pack(u32 tag, u32 v)
+	{
+		return (Word(tag) << 32) | Word(v);
+	}
+	DEVFN u32 tag(Word w)
+	{
+		return u32(w >> 32);
+	}
+	DEVFN u32 value(Word w)
+	{
+		return u32(w);
+	}
+	DEVFN Word load(const char* base, size_t tile)
+	{
+		return *reinterpret_cast<const volatile Word*>(base + tile * 16);
+	}
+	DEVFN void store(char* base, size_t tile, Word w)
+	{
+		*reinterpret_cast<volatile Word*>(base + tile * 16) = w;
+	}
+};
+
+template <>
+struct ScanDesc<u64>
+{
+	typedef ulonglong2 Word;
+	DEVFN Word pack(u32 tag, u64 v)
+	{
+		Word w;
+		w.x = v;
+		w.y = tag;
+		return w;
+	}
+	DEVFN u32 tag(Word w)
+	{
+		return u32(w.y);
+	}
+	DEVFN u64 value(Word w)
+	{
+		return w.x;
+	}
+	// one aligned 16-byte access: value and tag travel together
+	DEVFN Word load(const char* base, size_t tile)
+	{
+		Word w;
+		asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(base + tile * 16) : "memory");
+		return w;
+	}
+	DEVFN void store(char* base, size_t tile, Word w)
+	{
+		asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(base + tile * 16), "l"(w.x), "l"(w.y) : "memory");
+	}
+};
+
+// Called by all 32 lanes of warp 0 with the tile's aggregate; returns the tile's exclusive prefix (valid in every lane) and
+// publishes the tile's inclusive prefix. desc: 16 bytes per tile. Combine(a, b): a precedes b.
 template <typename T, typename Op>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const T* __restrict__ in, T* __restrict__ out, size_t n, u32* flags, char* aggregate, char* inclusive, u32 epoch, T* __restrict__ total_out)
+DEVFN T scan_chain_lookback_packed(u32 tile, const T& tile_aggregate, char* desc, u32 epoch)
+{
+	typedef ScanDesc<T> D;
+	const int lane = threadIdx.x & 31;
+	const u32 tag_agg = (epoch << 2) | 1u, tag_inc = (epoch << 2) | 2u;
+	if (tile == 0)
+	{
+		if (lane == 0)
+			D::store(desc, 0, D::pack(tag_inc, tile_aggregate));
+		return Op::identity();
+	}
+	const bool independent = Op::prefix_independent(tile_aggregate);
+	if (lane == 0)
+		D::store(desc, tile, D::pack(independent ? tag_inc : tag_agg, tile_aggregate));
+	T prefix = Op::identity();
+	int p = int(tile) - 1;
+	for (;;)
+	{
+		// lane L looks at tiles p - L*SCAN_LOOK - k, k = 0..SCAN_LOOK-1 (k = 0 nearest)
+		u32 tags[SCAN_LOOK];
+		T vals[SCAN_LOOK];
+		for (;;)
+		{
+			bool ready = true;
+#pragma unroll
+			for (int k = 0; k < SCAN_LOOK; ++k)
+			{
+				int idx = p - lane * SCAN_LOOK - k;
+				if (idx >= 0)
+				{
+					typename D::Word w = D::load(desc, size_t(idx));
+					tags[k] = D::tag(w);
+					vals[k] = D::value(w);
+				}
+				else
+				{
+					tags[k] = tag_inc;
+					vals[k] = Op::identity();
+				}
+				ready = ready && (tags[k] == tag_agg || tags[k] == tag_inc);
+			}
+			if (__all_sync(0xffffffffu, ready))
+				break;
+		}
+		// nearest inclusive prefix inside this lane, then across lanes
+		int local_inc = SCAN_LOOK;
+#pragma unroll
+		for (int k = SCAN_LOOK - 1; k >= 0; --k)
+			if (tags[k] == tag_inc)
+				local_inc = k;
+		unsigned inc_mask = __ballot_sync(0xffffffffu, local_inc < SCAN_LOOK);
+		int first_lane = inc_mask ? __ffs(inc_mask) - 1 : 32;
+		// ordered combination of this lane's descriptors up to (and including) the cut: farther back = left operand
+		T v = Op::identity();
+		if (lane <= first_lane)
+		{
+			int last = lane == first_lane ? local_inc : SCAN_LOOK - 1;
+#pragma unroll
+			for (int k = 0; k < SCAN_LOOK; ++k)
+				if (k <= last)
+					v = Op::apply(vals[k], v);
+		}
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			T t = shfl_down_struct(v, d);
+			if (lane + d < 32)
+				v = Op::apply(t, v);
+		}
+		v = shfl_idx_struct(v, 0);
+		prefix = Op::apply(v, prefix);
+		if (inc_mask)
+			break;
+		p -= 32 * SCAN_LOOK;
+	}
+	if (lane == 0 && !independent)
+		D::store(desc, tile, D::pack(tag_inc, Op::apply(prefix, tile_aggregate)));
+	return prefix;
+}
+
+template <typename T, typename Op, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_scan_chained(const T* __restrict__ in, T* __restrict__ out, size_t n, char* desc, u32 epoch, T* __restrict__ total_out)
 {
 	__shared__ T smem[34];
 	__shared__ T s_prefix;
-	size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
-	T v[SCAN_ITEMS];
-	if (base + SCAN_ITEMS <= n)
+	const int TILE = THREADS * ITEMS;
+	size_t base = size_t(blockIdx.x) * TILE + size_t(threadIdx.x) * ITEMS;
+	T v[ITEMS];
+	if (base + ITEMS <= n)
 	{
-		// SCAN_ITEMS contiguous elements per thread: 16-byte vector loads
+		// ITEMS contiguous elements per thread: 16-byte vector loads
 		const uint4* src = reinterpret_cast<const uint4*>(in + base);
 		uint4* dst = reinterpret_cast<uint4*>(v);
 #pragma unroll
-		for (int k = 0; k < int(sizeof(T) * SCAN_ITEMS / 16); ++k)
+		for (int k = 0; k < int(sizeof(T) * ITEMS / 16); ++k)
 			dst[k] = src[k];
 	}
 	else
 	{
 #pragma unroll
-		for (int k = 0; k < SCAN_ITEMS; ++k)
+		for (int k = 0; k < ITEMS; ++k)
 			v[k] = base + k < n ? in[base + k] : Op::identity();
 	}
 	T sum = Op::identity();
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k)
+	for (int k = 0; k < ITEMS; ++k)
 		sum = Op::apply(sum, v[k]);
 	T total;
 	T ex = block_exclusive_scan<T, Op>(sum, &total, smem);
 	if (threadIdx.x < 32)
 	{
-		T prefix = scan_chain_lookback<T, Op>(blockIdx.x, total, flags, aggregate, inclusive, epoch);
+		T prefix = scan_chain_lookback_packed<T, Op>(blockIdx.x, total, desc, epoch);
 		if (threadIdx.x == 0)
 		{
 			s_prefix = prefix;
@@ -368,24 +522,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const T* __restri
 	__syncthreads();
 	T run = Op::apply(s_prefix, ex);
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k)
+	for (int k = 0; k < ITEMS; ++k)
 	{
 		T t = v[k];
 		v[k] = run;
 		run = Op::apply(run, t);
 	}
-	if (base + SCAN_ITEMS <= n)
+	if (base + ITEMS <= n)
 	{
 		uint4* dst = reinterpret_cast<uint4*>(out + base);
 		const uint4* src = reinterpret_cast<const uint4*>(v);
 #pragma unroll
-		for (int k = 0; k < int(sizeof(T) * SCAN_ITEMS / 16); ++k)
+		for (int k = 0; k < int(sizeof(T) * ITEMS / 16); ++k)
 			dst[k] = src[k];
 	}
 	else
 	{
 #pragma unroll
-		for (int k = 0; k < SCAN_ITEMS; ++k)
+		for (int k = 0; k < ITEMS; ++k)
 			if (base + k < n)
 				out[base + k] = v[k];
 	}
@@ -393,6 +547,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const T* __restri
 
 // out[i] = op(in[0..i)), in-place allowed; optional device-side total. `in`/`out` must be 16-byte aligned (arena
 // allocations are 256-byte aligned).
+static const size_t SCAN_LARGE_N = size_t(1) << 21;
+static const int SCAN_LARGE_THREADS = 512;
+static const int SCAN_LARGE_ITEMS = 16;
 template <typename T, typename Op>
 static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena&)
 {
@@ -402,10 +559,20 @@ static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena
 			dev_memset(total, 0, sizeof(T));
 		return;
 	}
-	size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-	scan_chain_reserve(nblocks);
 	u32 epoch = scan_chain_next_epoch();
-	LAUNCH_GRID((k_scan_chained<T, Op>), nblocks, SCAN_THREADS, in, out, n, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch, total);
+	if (n >= SCAN_LARGE_N)
+	{
+		const size_t tile = size_t(SCAN_LARGE_THREADS) * SCAN_LARGE_ITEMS;
+		size_t nblocks = (n + tile - 1) / tile;
+		scan_chain_reserve(nblocks);
+		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>), nblocks, SCAN_LARGE_THREADS, in, out, n, g_scan_chain.desc, epoch, total);
+	}
+	else
+	{
+		size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+		scan_chain_reserve(nblocks);
+		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>), nblocks, SCAN_THREADS, in, out, n, g_scan_chain.desc, epoch, total);
+	}
 }
 
 // ---- radix sort ------------------------------------------------------------------------------------------------

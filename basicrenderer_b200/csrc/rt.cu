@@ -262,10 +262,13 @@ void scan_chain_reserve(size_t tiles)
 	dev_free(g_scan_chain.flags);
 	dev_free(g_scan_chain.aggregate);
 	dev_free(g_scan_chain.inclusive);
+	dev_free(g_scan_chain.desc);
 	g_scan_chain.flags = static_cast<u32*>(dev_malloc(cap * sizeof(u32)));
 	g_scan_chain.aggregate = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
 	g_scan_chain.inclusive = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
+	g_scan_chain.desc = static_cast<char*>(dev_malloc(cap * 16));
 	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.flags, 0, cap * sizeof(u32), g_stream));
+	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.desc, 0, cap * 16, g_stream));
 	g_scan_chain.capacity_tiles = cap;
 }
 #endif

@@ -1598,61 +1598,238 @@ KERNEL k_group_results(const GroupState* __restrict__ groups, const float* __res
 // de-indexed group (one "vertex" per corner), + meshopt_simplifyScale (:2934-2944). Callees: rescalePositions :550-606,
 // computeVertexIds :2083-2101, countTriangles :2103-2117, fillVertexCells :2119-2143, fillCellQuadrics :2165-2193,
 // fillCellRemap :2233-2248, filterTriangles :2278-2321, interpolate :2323-2329.
-// It runs only for groups whose edge-collapse result misses the target (rare), one group at a time; every step is a
-// data-parallel kernel over the group's corners, with the reference's sequential semantics recovered by
-//   * lowest-corner-wins hash tables (cell numbering, duplicate-triangle filter) + order preserving compaction,
+// All groups of the level whose edge-collapse result misses the target go through it together: their corners are laid out
+// back to back, every step is one data-parallel kernel over all of them, and the per-group grid-size search advances in
+// lock step with its state kept on the device (one host read per search round, not per group). The reference's sequential
+// semantics are recovered by
+//   * lowest-corner-wins hash tables (cell numbering, duplicate-triangle filter; one table region per group) + order
+//     preserving compaction,
 //   * per-cell quadric sums taken over the cell's corners in ascending corner order (the serial accumulation order),
 //   * (error, corner) lexicographic argmin per cell.
-KERNEL k_sl_minmax(const u32* __restrict__ corner_vertex, const float* __restrict__ positions, u32 n, u32* mm)
+struct SlGroup
+{
+	u32 tri_begin, tri_count; // in the concatenated triangle space of the fallback groups
+	u32 src_tri_begin;        // first triangle of the group in the level's merged index list
+	u32 target_tris;
+	u32 mm[6]; // order keys of min xyz / max xyz
+	float minv[3];
+	float extent, scale;
+	int min_grid, max_grid, next_grid, cur_grid;
+	u32 min_triangles, max_triangles;
+	u32 count; // non-degenerate triangles counted in the running search round
+	u32 phase; // 0 = initial count (grid 1) pending, 1 = searching, 2 = done
+	int pass;
+	u32 cell_table_base, cell_table_mask, tri_table_base, tri_table_mask;
+	u32 max_error_bits;
+	u32 kept;
+};
+
+// float -> int as x86-64 converts it (cvttss2si): out-of-range and NaN give INT_MIN. The reference's search runs on the host
+// CPU; CUDA's conversion saturates instead, which would steer the clamp the other way.
+DEVFN int x86_float_to_int(float f)
+{
+	if (!(f > -2147483648.f && f < 2147483648.f))
+		return int(0x80000000u);
+	return int(f);
+}
+
+KERNEL k_sl_gather_corners(const u32* __restrict__ gtri, const u32* __restrict__ tri_group, const SlGroup* __restrict__ groups, u32 n, u32* corner_vertex)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	u32 t = u32(i / 3);
+	const SlGroup& g = groups[tri_group[t]];
+	corner_vertex[i] = gtri[(size_t(g.src_tri_begin) + (t - g.tri_begin)) * 3 + (i - size_t(t) * 3)];
+}
+
+KERNEL k_sl_minmax(const u32* __restrict__ corner_vertex, const u32* __restrict__ tri_group, const float* __restrict__ positions, u32 n, SlGroup* groups)
 {
 	size_t i = GTID;
 	if (i >= n)
 		return;
 	const float* p = positions + size_t(corner_vertex[i]) * 3;
+	u32 g = tri_group[i / 3];
+#ifndef CLODB_EMU
+	unsigned active = __activemask();
+	u32 g0 = __shfl_sync(active, g, __ffs(active) - 1);
+	if (active == 0xffffffffu && __all_sync(active, g == g0))
+	{
+		for (int k = 0; k < 3; ++k)
+		{
+			u32 key = float_order_key(p[k]);
+			u32 lo = key, hi = key;
+			for (int d = 16; d >= 1; d >>= 1)
+			{
+				u32 olo = __shfl_xor_sync(0xffffffffu, lo, d), ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+				lo = olo < lo ? olo : lo;
+				hi = ohi > hi ? ohi : hi;
+			}
+			if ((threadIdx.x & 31) == 0)
+			{
+				atomicMin(&groups[g].mm[k], lo);
+				atomicMax(&groups[g].mm[3 + k], hi);
+			}
+		}
+		return;
+	}
+#endif
 	for (int k = 0; k < 3; ++k)
 	{
-		atomicMin(&mm[k], float_order_key(p[k]));
-		atomicMax(&mm[3 + k], float_order_key(p[k]));
+		atomicMin(&groups[g].mm[k], float_order_key(p[k]));
+		atomicMax(&groups[g].mm[3 + k], float_order_key(p[k]));
 	}
 }
 
-KERNEL k_sl_rescale(const u32* __restrict__ corner_vertex, const float* __restrict__ positions, u32 n, float minx, float miny, float minz, float scale, Vector3* vpos)
+// rescalePositions extent/scale + the start of the grid-size search (simplifier.cpp:2690-2703)
+KERNEL k_sl_setup(SlGroup* groups, u32 S)
+{
+	size_t s = GTID;
+	if (s >= S)
+		return;
+	SlGroup& g = groups[s];
+	float extent = 0.f;
+	for (int k = 0; k < 3; ++k)
+	{
+		float mn = float_from_order_key(g.mm[k]), mx = float_from_order_key(g.mm[3 + k]);
+		g.minv[k] = mn;
+		extent = (mx - mn) < extent ? extent : (mx - mn);
+	}
+	g.extent = extent;
+	g.scale = extent == 0 ? 0.f : 1.f / extent;
+	size_t target_index_count = size_t(g.target_tris) * 3;
+	size_t target_cell_count = target_index_count / 6;
+	g.min_grid = 1;
+	g.max_grid = 1025;
+	g.max_triangles = g.tri_count;
+	g.min_triangles = 0;
+	g.next_grid = x86_float_to_int(sqrtf(float(target_cell_count)) + 0.5f);
+	g.cur_grid = 1;
+	g.count = 0;
+	g.phase = 0;
+	g.pass = 0;
+	g.max_error_bits = 0;
+	g.kept = 0;
+}
+
+KERNEL k_sl_rescale(const u32* __restrict__ corner_vertex, const u32* __restrict__ tri_group, const SlGroup* __restrict__ groups, const float* __restrict__ positions, u32 n, Vector3* vpos)
 {
 	size_t i = GTID;
 	if (i >= n)
 		return;
+	const SlGroup& g = groups[tri_group[i / 3]];
 	const float* p = positions + size_t(corner_vertex[i]) * 3;
 	Vector3 r;
-	r.x = (p[0] - minx) * scale;
-	r.y = (p[1] - miny) * scale;
-	r.z = (p[2] - minz) * scale;
+	r.x = (p[0] - g.minv[0]) * g.scale;
+	r.y = (p[1] - g.minv[1]) * g.scale;
+	r.z = (p[2] - g.minv[2]) * g.scale;
 	vpos[i] = r;
 }
 
-KERNEL k_sl_ids(const Vector3* __restrict__ vpos, const u32* __restrict__ corner_vertex, const u8* __restrict__ locks, u32 n, int grid_size, u32* ids)
+// computeVertexIds for one corner; locked corners keep an id of their own (corner index inside the group)
+DEVFN u32 sl_vertex_id(const Vector3& v, bool locked, u32 local_corner, int grid_size)
 {
-	size_t i = GTID;
-	if (i >= n)
-		return;
 	float cell_scale = float(grid_size - 1);
-	Vector3 v = vpos[i];
 	int xi = int(v.x * cell_scale + 0.5f);
 	int yi = int(v.y * cell_scale + 0.5f);
 	int zi = int(v.z * cell_scale + 0.5f);
-	if (locks && (locks[corner_vertex[i]] & 1))
-		ids[i] = (1u << 30) | u32(i);
-	else
-		ids[i] = (u32(xi) << 20) | (u32(yi) << 10) | u32(zi);
+	if (locked)
+		return (1u << 30) | local_corner;
+	return (u32(xi) << 20) | (u32(yi) << 10) | u32(zi);
 }
 
-KERNEL k_sl_count_triangles(const u32* __restrict__ ids, u32 T, u32* count)
+// one search round: countTriangles with every searching group's current grid size
+KERNEL k_sl_count_triangles(const Vector3* __restrict__ vpos, const u32* __restrict__ corner_vertex, const u8* __restrict__ locks, const u32* __restrict__ tri_group, SlGroup* groups, u32 T)
 {
 	size_t t = GTID;
 	if (t >= T)
 		return;
-	u32 a = ids[t * 3 + 0], b = ids[t * 3 + 1], c = ids[t * 3 + 2];
-	if ((a != b) & (a != c) & (b != c))
-		atomicAdd(count, 1u);
+	u32 gi = tri_group[t];
+	const SlGroup& g = groups[gi];
+	bool hit = false;
+	if (g.phase != 2)
+	{
+		u32 local = u32(t - g.tri_begin) * 3;
+		u32 id[3];
+		for (int k = 0; k < 3; ++k)
+			id[k] = sl_vertex_id(vpos[t * 3 + k], locks && (locks[corner_vertex[t * 3 + k]] & 1) != 0, local + k, g.cur_grid);
+		hit = (id[0] != id[1]) & (id[0] != id[2]) & (id[1] != id[2]);
+	}
+#ifndef CLODB_EMU
+	// triangles of a group are contiguous: one atomic per warp and group
+	unsigned active = __activemask();
+	unsigned peers = __match_any_sync(active, gi);
+	unsigned votes = __ballot_sync(active, hit) & peers;
+	if (votes && (threadIdx.x & 31) == __ffs(peers) - 1)
+		atomicAdd(&groups[gi].count, u32(__popc(votes)));
+#else
+	if (hit)
+		atomicAdd(&groups[gi].count, 1u);
+#endif
+}
+
+// three point interpolation of the grid-size search (simplifier.cpp:2323-2329)
+DEVFN float sloppy_interpolate(float y, float x0, float y0, float x1, float y1, float x2, float y2)
+{
+	float num = (y1 - y) * (x1 - x2) * (x1 - x0) * (y2 - y0);
+	float den = (y2 - y) * (x1 - x2) * (y0 - y1) + (y0 - y) * (x1 - x0) * (y1 - y2);
+	return x1 + (den == 0.f ? 0.f : num / den);
+}
+
+// guided search for the grid size (simplifier.cpp:2697-2741; target_error = FLT_MAX => min_grid = 1), one step per round
+KERNEL k_sl_search_step(SlGroup* groups, u32 S, u32* any_searching)
+{
+	size_t s = GTID;
+	if (s >= S)
+		return;
+	SlGroup& g = groups[s];
+	if (g.phase == 2)
+		return;
+	const int kInterpolationPasses = 5;
+	size_t target_tris = (size_t(g.target_tris) * 3) / 3;
+	u32 triangles = g.count;
+	g.count = 0;
+	if (g.phase == 0)
+	{
+		g.min_triangles = triangles;
+		g.phase = 1;
+	}
+	else
+	{
+		int grid_size = g.cur_grid;
+		float tip = sloppy_interpolate(float(target_tris), float(g.min_grid), float(g.min_triangles), float(grid_size), float(triangles), float(g.max_grid), float(g.max_triangles));
+		if (triangles <= target_tris)
+		{
+			g.min_grid = grid_size;
+			g.min_triangles = triangles;
+		}
+		else
+		{
+			g.max_grid = grid_size;
+			g.max_triangles = triangles;
+		}
+		g.next_grid = (g.pass < kInterpolationPasses) ? x86_float_to_int(tip + 0.5f) : (g.min_grid + g.max_grid) / 2;
+		g.pass++;
+	}
+	if (g.pass >= 10 + kInterpolationPasses || g.min_triangles >= target_tris || g.max_grid - g.min_grid <= 1)
+	{
+		g.phase = 2;
+		g.cur_grid = g.min_grid;
+		return;
+	}
+	int grid_size = g.next_grid;
+	g.cur_grid = (grid_size <= g.min_grid) ? g.min_grid + 1 : (grid_size >= g.max_grid ? g.max_grid - 1 : grid_size);
+	*any_searching = 1u;
+}
+
+// hash table regions: per group, a power of two >= 2 * corners (cells) and >= 2 * triangles (duplicate filter)
+KERNEL k_sl_ids(const Vector3* __restrict__ vpos, const u32* __restrict__ corner_vertex, const u8* __restrict__ locks, const u32* __restrict__ tri_group, const SlGroup* __restrict__ groups, u32 n, u32* ids)
+{
+	size_t i = GTID;
+	if (i >= n)
+		return;
+	const SlGroup& g = groups[tri_group[i / 3]];
+	ids[i] = sl_vertex_id(vpos[i], locks && (locks[corner_vertex[i]] & 1) != 0, u32(i) - g.tri_begin * 3, g.min_grid);
 }
 
 DEVFN u32 sl_hash(u32 h)
@@ -1663,23 +1840,27 @@ DEVFN u32 sl_hash(u32 h)
 	return h;
 }
 
-// cell table: lowest corner per distinct vertex id
-KERNEL k_sl_cell_insert(const u32* __restrict__ ids, u32 n, u32* table_id, u32* table_first, u32 mask, u32* slot_of)
+// cell table: lowest corner per distinct vertex id of a group (groups whose search ended at zero triangles are skipped)
+KERNEL k_sl_cell_insert(const u32* __restrict__ ids, const u32* __restrict__ tri_group, const SlGroup* __restrict__ groups, u32 n, u32* table_id, u32* table_first, u32* slot_of)
 {
 	size_t i = GTID;
 	if (i >= n)
 		return;
+	const SlGroup& g = groups[tri_group[i / 3]];
+	slot_of[i] = 0xffffffffu;
+	if (g.min_triangles == 0)
+		return;
 	u32 id = ids[i];
-	u32 h = sl_hash(id) & mask;
+	u32 h = sl_hash(id) & g.cell_table_mask;
 	for (;;)
 	{
-		u32 old = atomicCAS(&table_id[h], 0xffffffffu, id);
+		u32 old = atomicCAS(&table_id[g.cell_table_base + h], 0xffffffffu, id);
 		if (old == 0xffffffffu || old == id)
 			break;
-		h = (h + 1) & mask;
+		h = (h + 1) & g.cell_table_mask;
 	}
-	atomicMin(&table_first[h], u32(i));
-	slot_of[i] = h;
+	atomicMin(&table_first[g.cell_table_base + h], u32(i));
+	slot_of[i] = g.cell_table_base + h;
 }
 
 KERNEL k_sl_first_flags(const u32* __restrict__ slot_of, const u32* __restrict__ table_first, u32 n, u32* flags)
@@ -1687,7 +1868,7 @@ KERNEL k_sl_first_flags(const u32* __restrict__ slot_of, const u32* __restrict__
 	size_t i = GTID;
 	if (i >= n)
 		return;
-	flags[i] = table_first[slot_of[i]] == u32(i) ? 1u : 0u;
+	flags[i] = (slot_of[i] != 0xffffffffu && table_first[slot_of[i]] == u32(i)) ? 1u : 0u;
 }
 
 KERNEL k_sl_assign_cells(const u32* __restrict__ slot_of, const u32* __restrict__ table_first, const u32* __restrict__ first_rank, u32 n, u32* cells)
@@ -1695,7 +1876,7 @@ KERNEL k_sl_assign_cells(const u32* __restrict__ slot_of, const u32* __restrict_
 	size_t i = GTID;
 	if (i >= n)
 		return;
-	cells[i] = first_rank[table_first[slot_of[i]]];
+	cells[i] = slot_of[i] != 0xffffffffu ? first_rank[table_first[slot_of[i]]] : 0xffffffffu;
 }
 
 // (cell, corner) entries of fillCellQuadrics: one per corner, or one (weight 3) for a triangle inside a single cell
@@ -1733,14 +1914,14 @@ KERNEL k_sl_cell_heads(const u32* __restrict__ sorted_cell, u32 n, u32* cell_beg
 }
 
 KERNEL k_sl_cell_quadrics(const u32* __restrict__ sorted_cell, const u32* __restrict__ sorted_corner, const u32* __restrict__ cell_begin, const u32* __restrict__ cells, const Vector3* __restrict__ vpos, u32 cell_count,
-    u32 valid_entries, Quadric* cell_quadrics)
+    u32 n, Quadric* cell_quadrics)
 {
 	size_t c = GTID;
 	if (c >= cell_count)
 		return;
 	Quadric Q;
 	quadric_zero(Q);
-	for (u32 e = cell_begin[c]; e < valid_entries && sorted_cell[e] == u32(c); ++e)
+	for (u32 e = cell_begin[c]; e < n && sorted_cell[e] == u32(c); ++e)
 	{
 		u32 corner = sorted_corner[e];
 		u32 t = corner / 3;
@@ -1759,28 +1940,31 @@ KERNEL k_sl_cell_remap(const u32* __restrict__ cells, const Quadric* __restrict_
 	if (i >= n)
 		return;
 	u32 cell = cells[i];
+	if (cell == 0xffffffffu)
+		return;
 	float error = quadric_error(cell_quadrics[cell], vpos[i]);
 	u64 key = (u64(__float_as_uint(error)) << 32) | u64(u32(i));
 	atomicMin(reinterpret_cast<unsigned long long*>(&cell_best[cell]), (unsigned long long)key);
 }
 
-KERNEL k_sl_max_error(const u64* __restrict__ cell_best, u32 cell_count, u32* max_bits)
+KERNEL k_sl_max_error(const u64* __restrict__ cell_best, const u32* __restrict__ tri_group, u32 cell_count, SlGroup* groups)
 {
 	size_t c = GTID;
 	if (c >= cell_count)
 		return;
-	atomicMax(max_bits, u32(cell_best[c] >> 32));
+	u64 best = cell_best[c];
+	atomicMax(&groups[tri_group[u32(best) / 3]].max_error_bits, u32(best >> 32));
 }
 
 // rotated (lowest corner id first) output triple per non-degenerate triangle; duplicates keep their first occurrence
-KERNEL k_sl_triangles(const u32* __restrict__ cells, const u64* __restrict__ cell_best, u32 T, u32* triple, u64* table_key, u32* table_first, u32 mask, u32* slot_of)
+KERNEL k_sl_triangles(const u32* __restrict__ cells, const u64* __restrict__ cell_best, const u32* __restrict__ tri_group, const SlGroup* __restrict__ groups, u32 T, u32* triple, u64* table_key, u32* table_first, u32* slot_of)
 {
 	size_t t = GTID;
 	if (t >= T)
 		return;
 	u32 c0 = cells[t * 3 + 0], c1 = cells[t * 3 + 1], c2 = cells[t * 3 + 2];
 	slot_of[t] = 0xffffffffu;
-	if (!(c0 != c1 && c0 != c2 && c1 != c2))
+	if (c0 == 0xffffffffu || !(c0 != c1 && c0 != c2 && c1 != c2))
 		return;
 	u32 a = u32(cell_best[c0]), b = u32(cell_best[c1]), c = u32(cell_best[c2]);
 	if (b < a && b < c)
@@ -1796,18 +1980,21 @@ KERNEL k_sl_triangles(const u32* __restrict__ cells, const u64* __restrict__ cel
 	triple[t * 3 + 0] = a;
 	triple[t * 3 + 1] = b;
 	triple[t * 3 + 2] = c;
-	// corner ids of a group are < 2^21 (checked by the caller), so the triple packs exactly into one 64-bit key
-	u32 h = ((a * 73856093u) ^ (b * 19349663u) ^ (c * 83492791u)) & mask;
-	u64 key = (u64(a) << 42) | (u64(b) << 21) | u64(c);
+	// corner ids inside a group are < 2^21 (checked by the caller), so the group-local triple packs exactly into one 64-bit key
+	const SlGroup& g = groups[tri_group[t]];
+	u32 base = g.tri_begin * 3;
+	u32 la = a - base, lb = b - base, lc = c - base;
+	u32 h = ((la * 73856093u) ^ (lb * 19349663u) ^ (lc * 83492791u)) & g.tri_table_mask;
+	u64 key = (u64(la) << 42) | (u64(lb) << 21) | u64(lc);
 	for (;;)
 	{
-		u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&table_key[h]), ~0ull, (unsigned long long)key);
+		u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&table_key[g.tri_table_base + h]), ~0ull, (unsigned long long)key);
 		if (old == ~0ull || old == key)
 			break;
-		h = (h + 1) & mask;
+		h = (h + 1) & g.tri_table_mask;
 	}
-	atomicMin(&table_first[h], u32(t));
-	slot_of[t] = h;
+	atomicMin(&table_first[g.tri_table_base + h], u32(t));
+	slot_of[t] = g.tri_table_base + h;
 }
 
 KERNEL k_sl_keep_flags(const u32* __restrict__ slot_of, const u32* __restrict__ table_first, u32 T, u32* keep)
@@ -1818,6 +2005,7 @@ KERNEL k_sl_keep_flags(const u32* __restrict__ slot_of, const u32* __restrict__ 
 	keep[t] = (slot_of[t] != 0xffffffffu && table_first[slot_of[t]] == u32(t)) ? 1u : 0u;
 }
 
+// kept triangles of all fallback groups, compacted in order (so group by group): global vertex ids
 KERNEL k_sl_emit(const u32* __restrict__ triple, const u32* __restrict__ keep_scanned, u32 total, const u32* __restrict__ corner_vertex, u32 T, u32* out_tri)
 {
 	size_t t = GTID;
@@ -1827,21 +2015,43 @@ KERNEL k_sl_emit(const u32* __restrict__ triple, const u32* __restrict__ keep_sc
 	u32 next = t + 1 < T ? keep_scanned[t + 1] : total;
 	if (next == pos)
 		return;
-	out_tri[pos * 3 + 0] = corner_vertex[triple[t * 3 + 0]];
-	out_tri[pos * 3 + 1] = corner_vertex[triple[t * 3 + 1]];
-	out_tri[pos * 3 + 2] = corner_vertex[triple[t * 3 + 2]];
+	out_tri[size_t(pos) * 3 + 0] = corner_vertex[triple[t * 3 + 0]];
+	out_tri[size_t(pos) * 3 + 1] = corner_vertex[triple[t * 3 + 1]];
+	out_tri[size_t(pos) * 3 + 2] = corner_vertex[triple[t * 3 + 2]];
 }
 
-// three point interpolation of the grid-size search (simplifier.cpp:2323-2329)
-static float sloppy_interpolate(float y, float x0, float y0, float x1, float y1, float x2, float y2)
+KERNEL k_sl_group_kept(const u32* __restrict__ keep_scanned, u32 total, u32 T, SlGroup* groups, u32 S)
 {
-	float num = (y1 - y) * (x1 - x2) * (x1 - x0) * (y2 - y0);
-	float den = (y2 - y) * (x1 - x2) * (y0 - y1) + (y0 - y) * (x1 - x0) * (y1 - y2);
-	return x1 + (den == 0.f ? 0.f : num / den);
+	size_t s = GTID;
+	if (s >= S)
+		return;
+	SlGroup& g = groups[s];
+	u32 end = g.tri_begin + g.tri_count;
+	g.kept = (end < T ? keep_scanned[end] : total) - keep_scanned[g.tri_begin];
 }
 
-// One group: corner_vertex = the group's merged index list (T triangles). Writes the simplified triangles (global vertex
-// ids) to out_tri (capacity T) and returns their count; *out_error = absolute error (before the sloppy error factor).
+// level output after the fallback: group g takes its triangles either from the edge-collapse result or from the compacted
+// fallback output (src_is_fallback), new_offset gives the reassembled layout
+KERNEL k_sl_assemble(const u32* __restrict__ new_offset, const u32* __restrict__ src_begin, const u8* __restrict__ src_is_fallback, u32 G, const u32* __restrict__ collapsed_tri, const u32* __restrict__ fallback_tri, u32* out_tri, u32 total)
+{
+	size_t j = GTID;
+	if (j >= total)
+		return;
+	u32 lo = 0, hi = G;
+	while (hi - lo > 1)
+	{
+		u32 mid = (lo + hi) / 2;
+		if (new_offset[mid] <= u32(j))
+			lo = mid;
+		else
+			hi = mid;
+	}
+	const u32* src = (src_is_fallback[lo] ? fallback_tri : collapsed_tri) + (size_t(src_begin[lo]) + (j - new_offset[lo])) * 3;
+	out_tri[j * 3 + 0] = src[0];
+	out_tri[j * 3 + 1] = src[1];
+	out_tri[j * 3 + 2] = src[2];
+}
+
 static float host_uint_as_float(u32 u)
 {
 	float f;
@@ -1849,139 +2059,149 @@ static float host_uint_as_float(u32 u)
 	return f;
 }
 
-static float host_float_from_order_key(u32 k)
+struct SloppyResult
 {
-	return host_uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
+	u32* tri = nullptr; // kept triangles of the fallback groups back to back, in group order (temp arena)
+	std::vector<u32> kept;
+	std::vector<float> error; // absolute error per fallback group (before the sloppy error factor)
+};
 
-static u32 sloppy_group(const u32* corner_vertex, u32 T, u32 target_tris, const DeviceMesh& mesh, const u8* locks, u32* out_tri, float* out_error, Arena& temp)
+// sel: the groups of the level that take the fallback (ascending); group_tri_offset_host: the level's merged index list layout.
+static SloppyResult sloppy_groups(const u32* gtri, const u32* group_tri_offset_host, const std::vector<u32>& sel, const std::vector<u32>& target_tris, const DeviceMesh& mesh, const u8* locks, Arena& temp)
 {
-	ArenaScope scope(temp);
-	u32 n = T * 3;
-	if (n >= (1u << 21))
-		throw Error("clodb200: sloppy fallback supports groups of up to 699050 triangles");
-	size_t target_index_count = size_t(target_tris) * 3;
-	size_t target_cell_count = target_index_count / 6;
+	SloppyResult res;
+	u32 S = u32(sel.size());
+	std::vector<SlGroup> host(S);
+	u64 T64 = 0, cell_table_total = 0, tri_table_total = 0;
+	for (u32 s = 0; s < S; ++s)
+	{
+		SlGroup& g = host[s];
+		memset(&g, 0, sizeof(g));
+		u32 Tg = group_tri_offset_host[sel[s] + 1] - group_tri_offset_host[sel[s]];
+		if (size_t(Tg) * 3 >= (1u << 21))
+			throw Error("clodb200: sloppy fallback supports groups of up to 699050 triangles");
+		g.tri_begin = u32(T64);
+		g.tri_count = Tg;
+		g.src_tri_begin = group_tri_offset_host[sel[s]];
+		g.target_tris = target_tris[s];
+		for (int k = 0; k < 3; ++k)
+			g.mm[k] = 0xffffffffu;
+		size_t cells = 1, tris = 1;
+		while (cells < size_t(Tg) * 6)
+			cells <<= 1;
+		while (tris < size_t(Tg) * 2)
+			tris <<= 1;
+		g.cell_table_base = u32(cell_table_total);
+		g.cell_table_mask = u32(cells - 1);
+		g.tri_table_base = u32(tri_table_total);
+		g.tri_table_mask = u32(tris - 1);
+		cell_table_total += cells;
+		tri_table_total += tris;
+		T64 += Tg;
+	}
+	if (T64 * 3 >= (u64(1) << 32) || cell_table_total >= (u64(1) << 32))
+		throw Error("clodb200: sloppy fallback batch exceeds 2^32 corners");
+	u32 T = u32(T64), n = T * 3;
+
+	SlGroup* groups = temp.alloc<SlGroup>(S);
+	dev_h2d(groups, host.data(), size_t(S) * sizeof(SlGroup));
+	u32* group_tri_begin = temp.alloc<u32>(size_t(S) + 1);
+	{
+		std::vector<u32> begins(size_t(S) + 1);
+		for (u32 s = 0; s < S; ++s)
+			begins[s] = host[s].tri_begin;
+		begins[S] = T;
+		dev_h2d(group_tri_begin, begins.data(), begins.size() * sizeof(u32));
+	}
 	u32* scalars = temp.alloc<u32>(8);
-
-	// rescalePositions over the de-indexed subset
-	u32 init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
-	dev_h2d(scalars, init, sizeof(init));
-	LAUNCH(k_sl_minmax, n, corner_vertex, mesh.positions, n, scalars);
-	std::vector<u32> mm = dev_download(scalars, 6);
-	float minv[3], maxv[3];
-	for (int k = 0; k < 3; ++k)
-	{
-		minv[k] = host_float_from_order_key(mm[k]);
-		maxv[k] = host_float_from_order_key(mm[3 + k]);
-	}
-	float extent = 0.f;
-	for (int k = 0; k < 3; ++k)
-		extent = (maxv[k] - minv[k]) < extent ? extent : (maxv[k] - minv[k]);
-	float scale = extent == 0 ? 0.f : 1.f / extent;
+	u32* tri_group = temp.alloc<u32>(T);
+	u32* corner_vertex = temp.alloc<u32>(n);
 	Vector3* vpos = temp.alloc<Vector3>(n);
-	LAUNCH(k_sl_rescale, n, corner_vertex, mesh.positions, n, minv[0], minv[1], minv[2], scale, vpos);
+	res.tri = temp.alloc<u32>(size_t(n) + 3);
+	LAUNCH(k_tri_group, T, group_tri_begin, S, tri_group, T);
+	LAUNCH(k_sl_gather_corners, n, gtri, tri_group, groups, n, corner_vertex);
 
-	u32* ids = temp.alloc<u32>(n);
-	auto count_triangles = [&](int grid) -> size_t {
-		LAUNCH(k_sl_ids, n, vpos, corner_vertex, locks, n, grid, ids);
-		dev_memset(scalars + 6, 0, sizeof(u32));
-		LAUNCH(k_sl_count_triangles, T, ids, T, scalars + 6);
-		return dev_read(scalars + 6);
-	};
+	// rescalePositions over the de-indexed subsets
+	LAUNCH(k_sl_minmax, n, corner_vertex, tri_group, mesh.positions, n, groups);
+	LAUNCH(k_sl_setup, S, groups, S);
+	LAUNCH(k_sl_rescale, n, corner_vertex, tri_group, groups, mesh.positions, n, vpos);
 
-	// guided search for the grid size (target_error = FLT_MAX => min_grid = 1; locks are always passed)
-	const int kInterpolationPasses = 5;
-	int min_grid = 1;
-	int max_grid = 1025;
-	size_t min_triangles = count_triangles(min_grid);
-	size_t max_triangles = T;
-	int next_grid_size = int(sqrtf(float(target_cell_count)) + 0.5f);
-	for (int pass = 0; pass < 10 + kInterpolationPasses; ++pass)
+	// grid-size search: initial count at grid 1 + at most 15 guided rounds, all groups in lock step
+	for (int round = 0; round < 17; ++round)
 	{
-		if (min_triangles >= target_index_count / 3 || max_grid - min_grid <= 1)
+		LAUNCH(k_sl_count_triangles, T, vpos, corner_vertex, locks, tri_group, groups, T);
+		dev_memset(scalars, 0, sizeof(u32));
+		LAUNCH(k_sl_search_step, S, groups, S, scalars);
+		if (dev_read(scalars) == 0)
 			break;
-		int grid_size = next_grid_size;
-		grid_size = (grid_size <= min_grid) ? min_grid + 1 : (grid_size >= max_grid ? max_grid - 1 : grid_size);
-		size_t triangles = count_triangles(grid_size);
-		float tip = sloppy_interpolate(float(size_t(target_index_count / 3)), float(min_grid), float(min_triangles), float(grid_size), float(triangles), float(max_grid), float(max_triangles));
-		if (triangles <= target_index_count / 3)
-		{
-			min_grid = grid_size;
-			min_triangles = triangles;
-		}
-		else
-		{
-			max_grid = grid_size;
-			max_triangles = triangles;
-		}
-		next_grid_size = (pass < kInterpolationPasses) ? int(tip + 0.5f) : (min_grid + max_grid) / 2;
-	}
-	if (min_triangles == 0)
-	{
-		*out_error = 1.f * extent;
-		return 0;
 	}
 
+	ArenaScope scope(temp);
 	// cells in first-occurrence order
-	LAUNCH(k_sl_ids, n, vpos, corner_vertex, locks, n, min_grid, ids);
-	size_t table_size = 1;
-	while (table_size < size_t(n) * 2)
-		table_size <<= 1;
-	u32* table_id = temp.alloc<u32>(table_size);
-	u32* table_first = temp.alloc<u32>(table_size);
+	u32* ids = temp.alloc<u32>(n);
+	u32* table_id = temp.alloc<u32>(cell_table_total);
+	u32* table_first = temp.alloc<u32>(cell_table_total);
 	u32* slot_of = temp.alloc<u32>(n);
 	u32* flags = temp.alloc<u32>(size_t(n) + 1);
 	u32* cells = temp.alloc<u32>(n);
-	dev_memset(table_id, 0xff, table_size * 4);
-	dev_memset(table_first, 0xff, table_size * 4);
-	LAUNCH(k_sl_cell_insert, n, ids, n, table_id, table_first, u32(table_size - 1), slot_of);
+	LAUNCH(k_sl_ids, n, vpos, corner_vertex, locks, tri_group, groups, n, ids);
+	dev_memset(table_id, 0xff, cell_table_total * 4);
+	dev_memset(table_first, 0xff, cell_table_total * 4);
+	LAUNCH(k_sl_cell_insert, n, ids, tri_group, groups, n, table_id, table_first, slot_of);
 	LAUNCH(k_sl_first_flags, n, slot_of, table_first, n, flags);
 	exclusive_scan_u32(flags, flags, n, scalars + 6, temp);
 	u32 cell_count = dev_read(scalars + 6);
 	LAUNCH(k_sl_assign_cells, n, slot_of, table_first, flags, n, cells);
 
-	// per-cell quadrics, summed in ascending corner order
-	u32* entry_cell = temp.alloc<u32>(n);
-	u32* entry_corner = temp.alloc<u32>(n);
-	u32* entry_cell_tmp = temp.alloc<u32>(n);
-	u32* entry_corner_tmp = temp.alloc<u32>(n);
-	u32* cell_begin = temp.alloc<u32>(size_t(cell_count) + 1);
-	Quadric* cell_quadrics = temp.alloc<Quadric>(cell_count);
-	u64* cell_best = temp.alloc<u64>(cell_count);
-	LAUNCH(k_sl_quadric_entries, T, cells, T, entry_cell, entry_corner);
-	radix_sort_pairs<u32>(entry_cell, entry_cell_tmp, entry_corner, entry_corner_tmp, n, 0, 32, temp);
-	dev_memset(cell_begin, 0, (size_t(cell_count) + 1) * 4);
-	LAUNCH(k_sl_cell_heads, size_t(n) + 1, entry_cell, n, cell_begin, cell_count);
-	u32 valid_entries = dev_read(cell_begin + cell_count);
-	LAUNCH(k_sl_cell_quadrics, cell_count, entry_cell, entry_corner, cell_begin, cells, vpos, cell_count, valid_entries, cell_quadrics);
+	u32 kept_total = 0;
+	if (cell_count)
+	{
+		// per-cell quadrics, summed in ascending corner order
+		u32* entry_cell = ids; // ids, slot_of are dead from here on
+		u32* entry_corner = slot_of;
+		u32* entry_cell_tmp = temp.alloc<u32>(n);
+		u32* entry_corner_tmp = temp.alloc<u32>(n);
+		u32* cell_begin = temp.alloc<u32>(size_t(cell_count) + 1);
+		Quadric* cell_quadrics = temp.alloc<Quadric>(cell_count);
+		u64* cell_best = temp.alloc<u64>(cell_count);
+		LAUNCH(k_sl_quadric_entries, T, cells, T, entry_cell, entry_corner);
+		// keys are cell numbers or 0xffffffff (entries that do not count): all 32 bits take part
+		radix_sort_pairs<u32>(entry_cell, entry_cell_tmp, entry_corner, entry_corner_tmp, n, 0, 32, temp);
+		dev_memset(cell_begin, 0, (size_t(cell_count) + 1) * 4);
+		LAUNCH(k_sl_cell_heads, size_t(n) + 1, entry_cell, n, cell_begin, cell_count);
+		LAUNCH(k_sl_cell_quadrics, cell_count, entry_cell, entry_corner, cell_begin, cells, vpos, cell_count, n, cell_quadrics);
 
-	// best vertex per cell, error
-	dev_memset(cell_best, 0xff, size_t(cell_count) * 8);
-	LAUNCH(k_sl_cell_remap, n, cells, cell_quadrics, vpos, n, cell_best);
-	dev_memset(scalars + 7, 0, sizeof(u32));
-	LAUNCH(k_sl_max_error, cell_count, cell_best, cell_count, scalars + 7);
+		// best vertex per cell, error
+		dev_memset(cell_best, 0xff, size_t(cell_count) * 8);
+		LAUNCH(k_sl_cell_remap, n, cells, cell_quadrics, vpos, n, cell_best);
+		LAUNCH(k_sl_max_error, cell_count, cell_best, tri_group, cell_count, groups);
 
-	// triangles: drop degenerate and duplicate ones, keep order
-	size_t tt_size = 1;
-	while (tt_size < size_t(T) * 2)
-		tt_size <<= 1;
-	u32* triple = temp.alloc<u32>(n);
-	u64* tt_key = temp.alloc<u64>(tt_size);
-	u32* tt_first = temp.alloc<u32>(tt_size);
-	u32* tslot = temp.alloc<u32>(T);
-	u32* keep = temp.alloc<u32>(size_t(T) + 1);
-	dev_memset(tt_key, 0xff, tt_size * 8);
-	dev_memset(tt_first, 0xff, tt_size * 4);
-	LAUNCH(k_sl_triangles, T, cells, cell_best, T, triple, tt_key, tt_first, u32(tt_size - 1), tslot);
-	LAUNCH(k_sl_keep_flags, T, tslot, tt_first, T, keep);
-	exclusive_scan_u32(keep, keep, T, scalars + 6, temp);
-	u32 kept = dev_read(scalars + 6);
-	LAUNCH(k_sl_emit, T, triple, keep, kept, corner_vertex, T, out_tri);
+		// triangles: drop degenerate and duplicate ones, keep order
+		u32* triple = entry_cell_tmp;
+		u64* tt_key = temp.alloc<u64>(tri_table_total);
+		u32* tt_first = temp.alloc<u32>(tri_table_total);
+		u32* tslot = temp.alloc<u32>(T);
+		u32* keep = temp.alloc<u32>(size_t(T) + 1);
+		dev_memset(tt_key, 0xff, tri_table_total * 8);
+		dev_memset(tt_first, 0xff, tri_table_total * 4);
+		LAUNCH(k_sl_triangles, T, cells, cell_best, tri_group, groups, T, triple, tt_key, tt_first, tslot);
+		LAUNCH(k_sl_keep_flags, T, tslot, tt_first, T, keep);
+		exclusive_scan_u32(keep, keep, T, scalars + 6, temp);
+		kept_total = dev_read(scalars + 6);
+		LAUNCH(k_sl_emit, T, triple, keep, kept_total, corner_vertex, T, res.tri);
+		LAUNCH(k_sl_group_kept, S, keep, kept_total, T, groups, S);
+	}
 
-	float result_error = host_uint_as_float(dev_read(scalars + 7));
-	*out_error = sqrtf(result_error) * extent;
-	return kept;
+	host = dev_download(groups, S);
+	res.kept.resize(S);
+	res.error.resize(S);
+	for (u32 s = 0; s < S; ++s)
+	{
+		res.kept[s] = host[s].kept;
+		// a search that ends at zero triangles returns the empty mesh with error 1 (simplifier.cpp:2743-2750)
+		res.error[s] = host[s].min_triangles == 0 ? 1.f * host[s].extent : sqrtf(host_uint_as_float(host[s].max_error_bits)) * host[s].extent;
+	}
+	return res;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -2021,6 +2241,7 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 	u32* scalars = temp.alloc<u32>(8); // [0] totals, [1] any_active, [2] undecided
 
 	GroupState* groups = temp.alloc<GroupState>(G);
+	const size_t main_mark = temp.mark(); // allocations of the edge-collapse passes start here (released before the fallback)
 	dev_memset(scalars, 0, 8 * sizeof(u32));
 	LAUNCH(k_init_groups, G, groups, group_tri_offset, G, config.simplify_ratio, scalars + 1);
 
@@ -2334,40 +2555,49 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 	if (config.simplify_fallback_sloppy)
 	{
 		std::vector<GroupState> gh = dev_download(groups, G);
-		bool any = false;
+		std::vector<u32> sel, sel_target;
 		for (u32 g = 0; g < G; ++g)
-			any |= gh[g].tri_count > gh[g].target_tris;
-		if (any)
+			if (gh[g].tri_count > gh[g].target_tris)
+			{
+				sel.push_back(g);
+				sel_target.push_back(gh[g].target_tris);
+			}
+		if (!sel.empty())
 		{
-			std::vector<u32> new_offset(size_t(G) + 1, 0);
+			// everything the edge-collapse passes allocated is dead now (its results live in the persist arena)
+			temp.release(main_mark);
 			std::vector<float> new_error = dev_download(out.group_error, G);
-			std::vector<u32*> sloppy_tri(G, nullptr);
-			std::vector<u32> sloppy_count(G, 0);
-			for (u32 g = 0; g < G; ++g)
+			SloppyResult sl = sloppy_groups(gtri, group_tri_offset_host, sel, sel_target, mesh, locks, temp);
+			g_simplify_stats.sloppy_groups += u32(sel.size());
+			// reassemble the level output group by group (the fallback may return more or fewer triangles)
+			std::vector<u32> new_offset(size_t(G) + 1, 0), src_begin(G);
+			std::vector<u8> src_is_fallback(G, 0);
+			u32 fallback_begin = 0;
+			for (u32 g = 0, s = 0; g < G; ++g)
 			{
 				u32 count = gh[g].tri_count;
-				if (count > gh[g].target_tris)
+				src_begin[g] = gh[g].tri_begin;
+				if (s < sel.size() && sel[s] == g)
 				{
-					u32 Tg = group_tri_offset_host[g + 1] - group_tri_offset_host[g];
-					sloppy_tri[g] = temp.alloc<u32>(size_t(Tg) * 3); // lives until the scope of this call ends
-					float err = 0.f;
-					sloppy_count[g] = sloppy_group(gtri + size_t(group_tri_offset_host[g]) * 3, Tg, gh[g].target_tris, mesh, locks, sloppy_tri[g], &err, temp);
-					new_error[g] = err * config.simplify_error_factor_sloppy;
-					count = sloppy_count[g];
-					g_simplify_stats.sloppy_groups++;
+					count = sl.kept[s];
+					src_begin[g] = fallback_begin;
+					src_is_fallback[g] = 1;
+					fallback_begin += count;
+					new_error[g] = sl.error[s] * config.simplify_error_factor_sloppy;
+					++s;
 				}
 				new_offset[g + 1] = new_offset[g] + count;
 			}
-			// reassemble the level output group by group (the fallback may return more or fewer triangles)
-			u32* assembled = temp.alloc<u32>(size_t(new_offset[G]) * 3 + 3);
-			for (u32 g = 0; g < G; ++g)
-			{
-				u32 count = new_offset[g + 1] - new_offset[g];
-				const u32* src = sloppy_tri[g] ? sloppy_tri[g] : out.tri + size_t(gh[g].tri_begin) * 3;
-				dev_d2d(assembled + size_t(new_offset[g]) * 3, src, size_t(count) * 12);
-			}
 			if (size_t(new_offset[G]) > size_t(T))
 				throw Error("clodb200: sloppy fallback produced more triangles than its input");
+			u32* d_offset = temp.alloc<u32>(size_t(G) + 1);
+			u32* d_src_begin = temp.alloc<u32>(G);
+			u8* d_is_fallback = temp.alloc<u8>(G);
+			u32* assembled = temp.alloc<u32>(size_t(new_offset[G]) * 3 + 3);
+			dev_h2d(d_offset, new_offset.data(), (size_t(G) + 1) * 4);
+			dev_h2d(d_src_begin, src_begin.data(), size_t(G) * 4);
+			dev_h2d(d_is_fallback, src_is_fallback.data(), G);
+			LAUNCH(k_sl_assemble, new_offset[G], d_offset, d_src_begin, d_is_fallback, G, out.tri, sl.tri, assembled, new_offset[G]);
 			dev_d2d(out.tri, assembled, size_t(new_offset[G]) * 12);
 			dev_h2d(out.group_tri_offset, new_offset.data(), (size_t(G) + 1) * 4);
 			dev_h2d(out.group_error, new_error.data(), size_t(G) * 4);

@@ -276,6 +276,15 @@ float clodb200_timerStop(void);
 void clodb200_profileEnable(int enable);
 size_t clodb200_profileReport(char* buffer, size_t capacity);
 
+/* Device-wide primitives under the stages (hand-written single-pass chained scan and LSD radix sort, csrc/prims.cuh),
+ * exposed for their own parity tests and micro-benchmarks. Host pointers; the primitive runs `repeat` times and *ms
+ * (optional) receives the mean device time of the runs after the first. Scans are exclusive; the sort is stable on key
+ * bits [bit_lo, bit_hi) rounded up to whole 8-bit digits (callers keep the bits above bit_hi clear) and reorders `values`
+ * with the keys. */
+int clodb200_primExclusiveScanU32(const unsigned int* in, unsigned int* out, size_t n, unsigned int* total, int repeat, float* ms);
+int clodb200_primExclusiveMaxScanU64(const uint64_t* in, uint64_t* out, size_t n, int repeat, float* ms);
+int clodb200_primSortPairsU32(unsigned int* keys, unsigned int* values, size_t n, int bit_lo, int bit_hi, int repeat, float* ms);
+
 /* Diagnostics of the last clodb200_simplifyGroups / build on this process: {passes, wavefront rounds, max rounds in a pass}. */
 void clodb200_simplifyStats(unsigned int out3[3]);
 
