@@ -117,6 +117,7 @@ class ClodLib:
         L.clodb200_launch_count.restype = C.c_uint64
         L.clodb200_builderConfig.restype = Config
         L.clodb200_generatePositionRemap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.clodb200_generateMikkTangents.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
         L.clodb200_clusterize.argtypes = [C.POINTER(Config), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         L.clodb200_computeClusterBounds.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         L.clodb200_lockBoundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -175,6 +176,13 @@ class ClodLib:
         self._check(self._lib.clodb200_primSortPairsU32(_ptr(keys), _ptr(values), keys.size, bit_lo, bit_hi, repeat, C.byref(ms)))
         return keys, values, ms.value
 
+    def prim_acosf(self, values: np.ndarray) -> np.ndarray:
+        values = np.ascontiguousarray(values, np.float32)
+        out = np.zeros_like(values)
+        self._lib.clodb200_primAcosf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        self._check(self._lib.clodb200_primAcosf(_ptr(values), _ptr(out), values.size))
+        return out
+
     def position_remap(self, positions: np.ndarray, stride: int | None = None, vertex_count: int | None = None) -> np.ndarray:
         if stride is None:
             positions = np.ascontiguousarray(positions, dtype=np.float32)
@@ -182,6 +190,20 @@ class ClodLib:
         remap = np.empty(vertex_count, dtype=np.uint32)
         self._check(self._lib.clodb200_generatePositionRemap(_ptr(remap), _ptr(positions), vertex_count, stride))
         return remap
+
+    def mikk_tangents(self, vertices: np.ndarray, indices: np.ndarray, corners: bool = False):
+        """GenerateMikkTangents (ClusterLODUtilities.cpp:655-737) on the interleaved [V, stride/4] float stream (pos, normal, uv, ...).
+        Returns [V, 4] {tangent xyz, sign}, or None where the reference's generator refuses the input."""
+        vertices = np.ascontiguousarray(vertices, np.float32)
+        indices = np.ascontiguousarray(indices, np.uint32)
+        out = np.zeros((vertices.shape[0], 4), np.float32)
+        ok = C.c_int(0)
+        per_corner = np.zeros((indices.size, 4), np.float32) if corners else None
+        self._check(self._lib.clodb200_generateMikkTangents(_ptr(vertices), vertices.shape[0], vertices.shape[1] * 4 if vertices.ndim == 2 else 0, _ptr(indices), indices.size, _ptr(out), C.byref(ok),
+                                                            _ptr(per_corner) if corners else None))
+        if not ok.value:
+            return (None, None) if corners else None
+        return (out, per_corner) if corners else out
 
     def clusterize(self, positions: np.ndarray, indices: np.ndarray, segment_offsets=None, config: Config | None = None):
         """-> (cluster_index_offsets[K+1], cluster_vertex_counts[K], cluster_segments[K], indices[index_count])"""

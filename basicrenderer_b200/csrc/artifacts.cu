@@ -134,6 +134,20 @@ KERNEL k_split_vertex_streams(const u8* __restrict__ vertices, u32 stride, size_
 	}
 }
 
+KERNEL k_write_tangent_columns(const float* __restrict__ tangents4, size_t vertex_count, float* attributes, u32 attribute_stride, u32 tangent_column)
+{
+	size_t i = GTID;
+	if (i >= vertex_count)
+		return;
+	for (u32 j = 0; j < 4; ++j)
+		attributes[i * attribute_stride + tangent_column + j] = tangents4[i * 4 + j];
+}
+
+void write_tangent_columns(const float* tangents4, size_t vertex_count, float* attributes, u32 attribute_stride, u32 tangent_column)
+{
+	LAUNCH(k_write_tangent_columns, vertex_count, tangents4, vertex_count, attributes, attribute_stride, tangent_column);
+}
+
 void split_vertex_streams(const u8* vertices, u32 vertex_stride, size_t vertex_count, float* positions3, float* attributes, u32 attribute_stride, bool with_normals, const float* tangents4)
 {
 	LAUNCH(k_split_vertex_streams, vertex_count, vertices, vertex_stride, vertex_count, positions3, attributes, attribute_stride, with_normals ? 1u : 0u, tangents4);

@@ -48,9 +48,15 @@ struct DeviceGeometry
 	const float* uv_values[kMaxUvSets] = {}; // u at [i * uv_stride], v at [i * uv_stride + 1]
 	u32 uv_stride[kMaxUvSets] = {};          // in floats
 	DeviceMesh mesh;
+	// MikkTSpace tangents are generated inside every build call, as the reference does (ClusterLODUtilities.cpp:5359-5366):
+	// tangents4 = float4 per vertex scratch, attribute columns [tangent_column, +4) of mesh.attributes receive them
+	float* generated_tangents4 = nullptr;
+	float* attributes_rw = nullptr;
+	u32 tangent_column = 0;
 };
 
 // positions3[i] = vertex position; attributes[i] = {normal xyz}{tangent xyzw} as selected (either may be skipped)
+void write_tangent_columns(const float* tangents4, size_t vertex_count, float* attributes, u32 attribute_stride, u32 tangent_column);
 void split_vertex_streams(const u8* vertices, u32 vertex_stride, size_t vertex_count, float* positions3, float* attributes, u32 attribute_stride, bool with_normals,
     const float* tangents4);
 

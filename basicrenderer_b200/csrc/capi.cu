@@ -278,6 +278,37 @@ int clodb200_generatePositionRemap(unsigned int* remap, const float* positions, 
 	});
 }
 
+int clodb200_generateMikkTangents(const void* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count,
+    float* out_tangents4, int* out_generated, float* out_corner_tangents4)
+{
+	return guarded([&]() -> int {
+		if (out_generated)
+			*out_generated = 0;
+		if (!vertices || !indices || !out_tangents4 || !out_generated)
+			return fail(CLODB200_ERR_INVALID, "clodb200_generateMikkTangents: invalid arguments");
+		if (vertex_count == 0 || index_count == 0 || vertex_stride < 32 || vertex_stride % 4)
+			return CLODB200_OK; // GenerateMikkTangents returns false (ClusterLODUtilities.cpp:665-675)
+		for (size_t i = 0; i < index_count; ++i)
+			if (indices[i] >= vertex_count)
+				return CLODB200_OK; // :677-683
+		ensure_workspace(vertex_count * (size_t(vertex_stride) + 16) + index_count * 20 + (1 << 20), mikk_temp_bytes(vertex_count, index_count));
+		u8* dv = g_ws.persist.alloc<u8>(vertex_count * vertex_stride);
+		u32* di = g_ws.persist.alloc<u32>(index_count);
+		float* dt = g_ws.persist.alloc<float>(vertex_count * 4);
+		dev_h2d(dv, vertices, vertex_count * vertex_stride);
+		dev_h2d(di, indices, index_count * 4);
+		float* dc = out_corner_tangents4 ? g_ws.persist.alloc<float>(index_count * 4) : nullptr;
+		if (mikk_tangents(dv, vertex_stride, vertex_count, di, index_count, dt, g_ws.temp, dc))
+		{
+			dev_d2h(out_tangents4, dt, vertex_count * 16);
+			if (dc)
+				dev_d2h(out_corner_tangents4, dc, index_count * 16);
+			*out_generated = 1;
+		}
+		return CLODB200_OK;
+	});
+}
+
 int clodb200_clusterize(const clodb200_config* config, const unsigned int* indices, size_t index_count, const unsigned int* segment_offsets, size_t segment_count,
     const float* positions, size_t vertex_count, size_t positions_stride,
     unsigned int* cluster_index_counts, unsigned int* cluster_vertex_counts, unsigned int* cluster_segments, unsigned int* out_indices, size_t* out_cluster_count)
@@ -912,25 +943,38 @@ static clodb200_device_geometry* upload_geometry_locked(const clodb200_geometry&
 		const bool has_normals = (g.vertex_flags & kVertexNormals) != 0 && g.vertex_stride >= 24;
 		const bool has_texcoords = (g.vertex_flags & kVertexTexcoords) != 0 && g.vertex_stride >= 32;
 		const bool use_normals = st.enable_normal_attribute_simplification && has_normals;
-		const bool wants_tangents = use_normals && has_texcoords;
-		if (wants_tangents && !g.tangents)
-			throw Error("clodb200: a vertex stream with normals and texcoords needs the MikkTSpace tangent stream (clodb200_geometry::tangents); tangent generation is not built in");
+		bool wants_tangents = use_normals && has_texcoords;
 		DeviceMesh& mesh = geo.mesh;
 		float* dpos = static_cast<float*>(block_alloc(V * 12, dg->allocations));
-		u32 acount = (use_normals ? 3u : 0u) + (wants_tangents ? 4u : 0u);
-		float* dattr = acount ? static_cast<float*>(block_alloc(V * acount * 4, dg->allocations)) : nullptr;
 		float* dtan = nullptr;
 		if (wants_tangents)
 		{
 			dtan = static_cast<float*>(block_alloc(V * 16, dg->allocations));
-			dev_h2d(dtan, g.tangents, V * 16);
+			if (g.tangents)
+				dev_h2d(dtan, g.tangents, V * 16);
+			else if (g.vertex_stride % 4 == 0 && g.index_count % 3 == 0)
+			{
+				// GenerateMikkTangents runs inside every build call, as in the reference (:5359-5366); see build_artifacts_locked
+				dev_memset(dtan, 0, V * 16);
+				geo.generated_tangents4 = dtan;
+			}
+			else
+			{
+				// the generator refuses the input (:665-675): the build goes on without tangent attributes
+				wants_tangents = false;
+				dtan = nullptr;
+			}
 		}
+		u32 acount = (use_normals ? 3u : 0u) + (wants_tangents ? 4u : 0u);
+		float* dattr = acount ? static_cast<float*>(block_alloc(V * acount * 4, dg->allocations)) : nullptr;
 		split_vertex_streams(dv, g.vertex_stride, V, dpos, dattr, acount, use_normals, dtan);
 		mesh.positions = dpos;
 		mesh.vertex_count = V;
 		if (acount)
 		{
 			mesh.attributes = dattr;
+			geo.attributes_rw = dattr;
+			geo.tangent_column = use_normals ? 3u : 0u;
 			mesh.attribute_stride = acount;
 			mesh.attribute_count = acount;
 			u32 k = 0;
@@ -985,7 +1029,17 @@ static clodb200_artifacts* build_artifacts_locked(const clodb200_device_geometry
 		size_t scale_temp = 640, scale_persist = 96;
 		if (const char* e = getenv("CLODB200_TEMP_BYTES_PER_TRI"))
 			scale_temp = size_t(atoll(e));
-		ensure_workspace(T * scale_persist + V * 32 + (64u << 20), T * scale_temp + V * 16 + (64u << 20));
+		size_t temp_bytes = T * scale_temp + V * 16 + (64u << 20);
+		const DeviceGeometry& geo = dg->geometry;
+		if (geo.generated_tangents4)
+			temp_bytes = std::max(temp_bytes, mikk_temp_bytes(V, geo.index_count));
+		ensure_workspace(T * scale_persist + V * 32 + (64u << 20), temp_bytes);
+		if (geo.generated_tangents4)
+		{
+			if (!mikk_tangents(geo.vertices, geo.vertex_stride, V, geo.indices, geo.index_count, geo.generated_tangents4, g_ws.temp))
+				throw Error("clodb200: tangent generation refused an input that passed the upload checks");
+			write_tangent_columns(geo.generated_tangents4, V, geo.attributes_rw, geo.mesh.attribute_stride, geo.tangent_column);
+		}
 		build_artifacts(dg->geometry, dg->settings, g_ws, a->data, g_last_build_stats);
 		a->data.stats[12] = g_launches;
 	}
@@ -1266,6 +1320,21 @@ int clodb200_primExclusiveScanU32(const unsigned int* in, unsigned int* out, siz
 			dev_d2h(total, dtotal, sizeof(u32));
 		if (ms)
 			*ms = t;
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_primAcosf(const float* in, float* out, size_t n)
+{
+	return guarded([&]() -> int {
+		if (n && (!in || !out))
+			return fail(CLODB200_ERR_INVALID, "clodb200_primAcosf: invalid arguments");
+		ensure_workspace(n * 8 + (1 << 20), 1 << 20);
+		float* din = g_ws.persist.alloc<float>(n + 1);
+		float* dout = g_ws.persist.alloc<float>(n + 1);
+		dev_h2d(din, in, n * sizeof(float));
+		mikk_acosf(din, dout, n);
+		dev_d2h(out, dout, n * sizeof(float));
 		return CLODB200_OK;
 	});
 }

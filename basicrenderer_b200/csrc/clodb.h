@@ -56,6 +56,14 @@ void position_remap(const float* positions, size_t vertex_count, u32* remap, Are
 // locks[i] |= 2 where a protected attribute differs from the canonical vertex (clusterlod.h:829-841)
 void protect_bits(const float* attributes, u32 attribute_stride, u32 protect_mask, const u32* remap, size_t vertex_count, u8* locks);
 
+// ---- a1: MikkTSpace tangent stream (mikk.cu) -------------------------------------------------------------------------
+// GenerateMikkTangents (ClusterLODUtilities.cpp:655-737) over the interleaved vertex buffer (pos @0, normal @12, uv @24).
+// Writes float4 {tangent xyz, sign} per vertex; false where the reference's generator would refuse the input.
+// corner_tangents4 (optional, parity tests): the per-corner values handed to m_setTSpaceBasic, zeros for degenerate triangles.
+size_t mikk_temp_bytes(size_t vertex_count, size_t index_count);
+void mikk_acosf(const float* in, float* out, size_t n); // the corner-angle acosf on its own, for its parity test
+bool mikk_tangents(const u8* vertices, u32 vertex_stride, size_t vertex_count, const u32* indices, size_t index_count, float* tangents4, Arena& temp, float* corner_tangents4 = nullptr);
+
 // ---- S3: spatial clusterization (clusterize.cu) ---------------------------------------------------------------------
 // Splits every segment [seg_offsets[s], seg_offsets[s+1]) of the triangle list independently into meshlets, exactly as
 // clod::clusterize -> meshopt_buildMeshletsSpatial + meshopt_optimizeMeshlet would for that segment's index list

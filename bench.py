@@ -115,11 +115,13 @@ def _workload(rank: int, world: int):
     Returns (mesh, tangents or None)."""
     if WORKLOAD == "C3":
         f = int(os.environ.get("CLODB200_BENCH_ICO_F", C3_F))
-        mesh, tangents = meshgen.icosphere_seams_torch(f, seed=42 + rank)
+        # the generator's analytic tangents are not used: the MikkTSpace tangent stream is generated inside every build call
+        # (csrc/mikk.cu), as the reference generates it inside BuildClusterLODArtifactsFromGeometry
+        mesh, _analytic_tangents = meshgen.icosphere_seams_torch(f, seed=42 + rank)
         import torch
 
         torch.cuda.empty_cache()
-        return mesh, tangents
+        return mesh, None
     seed = 1234 if world == 1 else 1234 + rank
     n = int(os.environ.get("CLODB200_BENCH_GRID", WORKLOAD_N))
     return meshgen.grid(n, seed=seed), None
@@ -152,12 +154,11 @@ def run_ours(args):
     T = mesh.triangle_count
     from basicrenderer_b200 import artifacts as art
 
-    if tangents is None:
+    if WORKLOAD != "C3":
         vertices = _pin(art.interleave(mesh.positions, mesh.normals))
         flags = art.VERTEX_NORMALS
     else:
         vertices = _pin(mesh.vertices)  # pos + normal + uv, 32-byte stride
-        tangents = _pin(tangents)
         flags = art.VERTEX_NORMALS | art.VERTEX_TEXCOORDS
     indices = _pin(mesh.indices)
 
@@ -273,7 +274,7 @@ def run_ours(args):
             "config": {
                 "workload": (f"C2: {T}-triangle displaced heightfield grid (n={int(round((T / 2) ** 0.5))}), pos+normal, full DAG to a single root cluster" if WORKLOAD != "C3" else
                              f"C3: {T}-triangle noisy displaced icosphere (f={int(round((T / 20) ** 0.5))}) with normals + per-face UV atlas seams, 7 simplification attributes (normal + tangent xyz + sign), "
-                             "full DAG to a single root cluster; tangent stream supplied by the caller (analytic), the reference generates MikkTSpace tangents inside its call")
+                             "full DAG to a single root cluster; MikkTSpace tangents generated inside the timed call, as in the reference")
                             + ("" if world == 1 else f"; one such mesh per GPU ({world} independent meshes, sharded by mesh)"),
                 "builder": "clodDefaultConfig(128) + BasicRenderer overrides (128/128/64, partition 384, 8 refined ids, spatial clusters)",
                 "l2": "inputs and per-level working sets (>= 240 MB) exceed the 126 MB L2; no explicit flush",

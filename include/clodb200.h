@@ -75,6 +75,16 @@ clodb200_config clodb200_builderConfig(void);
 /* remap[i] = lowest index with the same position (IEEE ==). positions_stride in bytes (>= 12, multiple of 4). */
 int clodb200_generatePositionRemap(unsigned int* remap, const float* positions, size_t vertex_count, size_t positions_stride);
 
+/* GenerateMikkTangents (ClusterLODUtilities.cpp:655-737; genTangSpaceDefault of Utilities/mikktspace.cpp over the
+ * indexed triangle list, then the per-vertex sum in (face, corner) order, normalisation and the normal-derived fallback).
+ * `vertices` is the interleaved MeshVertexLayout stream with normals and texcoords (position @0, normal @12, uv @24;
+ * vertex_stride >= 32). out_tangents4 receives {tangent xyz, sign} per vertex. *out_generated = 0 where the reference's
+ * generator returns false (the builder then continues without tangent attributes, :5361-5365). out_corner_tangents4
+ * (optional, index_count float4) receives what genTangSpace hands to m_setTSpaceBasic per (face, corner); corners of
+ * degenerate triangles, which copy from another corner (mikktspace.cpp:1820-1861), read as zeros there. */
+int clodb200_generateMikkTangents(const void* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count,
+    float* out_tangents4, int* out_generated, float* out_corner_tangents4);
+
 /* Splits each segment [segment_offsets[s], segment_offsets[s+1]) (in triangles) of `indices` into meshlets.
  * Outputs: cluster_index_counts/cluster_vertex_counts/cluster_segments hold one entry per cluster (capacity
  * index_count / 3 entries each), out_indices receives index_count cluster-major indices. Returns the cluster count in
@@ -212,9 +222,10 @@ typedef struct clodb200_uv_set
 
 /* The arguments of BuildClusterLODArtifactsFromGeometry as plain pointers. `vertices` is the interleaved stream of
  * MeshVertexLayout (Mesh/VertexLayout.h: position f32x3 @0, normal f32x3 @12, uv f32x2 @24 if VERTEX_TEXCOORDS, then
- * colour f32x3 if VERTEX_COLORS), vertex_flags the VertexFlags bits (Mesh/VertexFlags.h). `tangents` (float4 per vertex)
- * replaces the reference's internal GenerateMikkTangents (:655-737) and is required when the stream has normals and
- * texcoords and normal-attribute simplification is on; it may be NULL otherwise. Skinned meshes are not supported. */
+ * colour f32x3 if VERTEX_COLORS), vertex_flags the VertexFlags bits (Mesh/VertexFlags.h). `tangents` is normally NULL:
+ * when the stream has normals and texcoords and normal-attribute simplification is on, the MikkTSpace tangent stream is
+ * generated on the device as the reference's GenerateMikkTangents does inside its call (:655-737, :5359-5366). A
+ * non-NULL `tangents` (float4 per vertex) overrides the generator. Skinned meshes are not supported. */
 typedef struct clodb200_geometry
 {
 	const void* vertices;
@@ -284,6 +295,9 @@ size_t clodb200_profileReport(char* buffer, size_t capacity);
 int clodb200_primExclusiveScanU32(const unsigned int* in, unsigned int* out, size_t n, unsigned int* total, int repeat, float* ms);
 int clodb200_primExclusiveMaxScanU64(const uint64_t* in, uint64_t* out, size_t n, int repeat, float* ms);
 int clodb200_primSortPairsU32(unsigned int* keys, unsigned int* values, size_t n, int bit_lo, int bit_hi, int repeat, float* ms);
+/* The corner-angle arccosine of the tangent generator: the reference's `acos(float)` (Utilities/mikktspace.cpp:1421)
+ * resolves to the C library's acosf; out[i] must equal it bit for bit on [-1, 1] (NaN outside). */
+int clodb200_primAcosf(const float* in, float* out, size_t n);
 
 /* Diagnostics of the last clodb200_simplifyGroups / build on this process: {passes, wavefront rounds, max rounds in a pass}. */
 void clodb200_simplifyStats(unsigned int out3[3]);

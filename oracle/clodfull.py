@@ -73,6 +73,30 @@ def last_attributes() -> np.ndarray:
     return np.frombuffer((C.c_float * (v.value * a.value)).from_address(ptr), np.float32).reshape(v.value, a.value).copy()
 
 
+_mikk = None
+
+
+def mikk_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libclodref_mikk.so"))
+
+
+def mikk_tangents(vertices: np.ndarray, indices: np.ndarray, with_seconds: bool = False):
+    """The reference's GenerateMikkTangents (ClusterLODUtilities.cpp:655-737, compiled unmodified into libclodref_mikk.so by
+    oracle/ref_mikk_driver.cpp). Returns [V, 4] or None when the reference's generator returns false."""
+    global _mikk
+    if _mikk is None:
+        _mikk = C.CDLL(os.path.join(_HERE, "_ref", "libclodref_mikk.so"))
+        _mikk.clodref_mikk_tangents.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_double)]
+    vertices = np.ascontiguousarray(vertices, np.float32)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    out = np.zeros((vertices.shape[0], 4), np.float32)
+    sec = C.c_double(0)
+    ok = _mikk.clodref_mikk_tangents(vertices.ctypes.data_as(C.c_void_p), vertices.shape[0], vertices.shape[1] * 4, indices.ctypes.data_as(C.c_void_p), indices.size,
+                                     out.ctypes.data_as(C.c_void_p), C.byref(sec))
+    res = out if ok else None
+    return (res, sec.value) if with_seconds else res
+
+
 class Artifacts:
     def __init__(self, arrays, seconds):
         self.__dict__.update(arrays)

@@ -77,19 +77,22 @@ def test_artifacts_position_only_and_colors(lib, full_oracle, meshes):
 
 
 def test_artifacts_uv_seams_and_tangents(lib, full_oracle, meshes):
-    """normals + UV atlas (config C3 shape): 7 simplification attributes, UV bitstreams in the pages. The tangent stream is
-    the reference's own MikkTSpace output, captured from the attribute stream it hands to clodBuildEx."""
+    """normals + UV atlas (config C3 shape): 7 simplification attributes, UV bitstreams in the pages. The MikkTSpace tangent
+    stream is generated inside our call (csrc/mikk.cu) exactly as the reference does inside its own (:5359-5366): it must
+    equal the attribute stream the reference hands to clodBuildEx bit for bit, and the artifacts must be byte-identical."""
     m = meshes["ico16uv"]
     v = art.interleave(m.positions, m.normals, m.vertices[:, 6:8])
     flags = art.VERTEX_NORMALS | art.VERTEX_TEXCOORDS
     ref = full_oracle.build(v, m.indices, flags=flags, clodb200_lib=lib.path)
     attrs = full_oracle.last_attributes()
     assert attrs.shape == (m.vertex_count, 7)
-    ours = lib.build_artifacts(v, m.indices, flags, tangents=attrs[:, 3:7])
+    got = lib.mikk_tangents(v, m.indices)
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(attrs[:, 3:7]).view(np.uint32))
+    ours = lib.build_artifacts(v, m.indices, flags)
     assert ours.page_header(0)["uvSetCount"] == 1
     _assert_identical(ref, ours)
-    with pytest.raises(Exception, match="tangent"):
-        lib.build_artifacts(v, m.indices, flags)
+    # a caller-supplied stream overrides the generator
+    _assert_identical(ref, lib.build_artifacts(v, m.indices, flags, tangents=attrs[:, 3:7]))
 
 
 def test_artifacts_empty_geometry(lib):
