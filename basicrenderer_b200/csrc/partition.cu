@@ -9,13 +9,16 @@
 // B200 formulation. The reference merges one pair at a time off a heap (serial, and its hottest function). Here the same
 // objective is optimised bulk-synchronously: every round each open group picks its best admissible neighbour under the
 // same score, locally-dominant (mutually best) pairs merge, and the group graph is contracted with a sort + run-length
-// pass. Group sizes follow the same target/max rules, so the result satisfies the same invariants (<= max size, groups
+// pass (first level) and then, round by round, by hashing inside one persistent kernel. Group sizes follow the same target/max rules, so the result satisfies the same invariants (<= max size, groups
 // closed once they reach the target) but is not the same partition bit for bit. Everything downstream of the merge
 // (Morton ordering of groups, cluster order inside groups, refined-id cap) follows the reference exactly.
 #include "clodb.h"
 
 #include <cfloat>
 #include <algorithm>
+#ifndef CLODB_EMU
+#include <cooperative_groups.h>
+#endif
 
 namespace clodb
 {
@@ -200,49 +203,6 @@ DEVFN float merge_score(const GroupInfo& lo, const GroupInfo& hi, u32 shared, bo
 	return score;
 }
 
-// best admissible neighbour of every open group; edges ordered by (score desc, min id asc, max id asc)
-KERNEL k_pick_neighbor(const GroupInfo* __restrict__ info, const u32* __restrict__ edge_off, const u32* __restrict__ edge_dst, const u32* __restrict__ edge_w, u32 K, u32 target, u32 max_size, int use_bounds, u32* best, float* best_score_out, u32* min_size)
-{
-	size_t gg = GTID;
-	if (gg >= K)
-		return;
-	u32 g = u32(gg);
-	best[g] = NONE;
-	const GroupInfo& me = info[g];
-	if (me.size == 0 || me.size >= target)
-		return;
-	float best_score = 0.f;
-	u32 best_h = NONE;
-	for (u32 e = edge_off[g]; e < edge_off[g + 1]; ++e)
-	{
-		u32 h = edge_dst[e];
-		const GroupInfo& other = info[h];
-		if (other.size == 0 || other.size >= target)
-			continue;
-		if (me.size + other.size > max_size)
-			continue;
-		float score = g < h ? merge_score(me, other, edge_w[e], use_bounds != 0) : merge_score(other, me, edge_w[e], use_bounds != 0);
-		if (!(score > 0.f))
-			continue;
-		bool better = score > best_score;
-		if (!better && score == best_score && best_h != NONE)
-		{
-			u32 a0 = g < h ? g : h, a1 = g < h ? h : g;
-			u32 b0 = g < best_h ? g : best_h, b1 = g < best_h ? best_h : g;
-			better = a0 < b0 || (a0 == b0 && a1 < b1);
-		}
-		if (better)
-		{
-			best_score = score;
-			best_h = h;
-		}
-	}
-	best[g] = best_h;
-	best_score_out[g] = best_score;
-	if (best_h != NONE)
-		atomicMin(min_size, me.size);
-}
-
 // mergeBounds (partition.cpp:289-312)
 DEVFN void merge_bounds(GroupInfo& target, const GroupInfo& source)
 {
@@ -267,72 +227,6 @@ DEVFN void merge_bounds(GroupInfo& target, const GroupInfo& source)
 	}
 }
 
-// Smallest-first agglomeration, bulk-synchronous: groups within 2x of the smallest open size are "movers" this round.
-// A mover merges with its pick when the pick is mutual (both movers; the lower id survives), or when the pick is a
-// larger, non-moving group that selected it as its best proposer (one proposer per group per round).
-KERNEL k_propose(const GroupInfo* __restrict__ info, const u32* __restrict__ best, const float* __restrict__ best_score, u32 K, const u32* __restrict__ min_size, u64* claim)
-{
-	size_t gg = GTID;
-	if (gg >= K)
-		return;
-	u32 g = u32(gg);
-	u32 h = best[g];
-	if (h == NONE)
-		return;
-	u32 limit = *min_size * 2;
-	if (info[g].size > limit || info[h].size <= limit)
-		return; // only movers propose, and only to non-movers
-	u64 key = (u64(__float_as_uint(best_score[g])) << 32) | u64(~g);
-	atomicMax(reinterpret_cast<unsigned long long*>(&claim[h]), (unsigned long long)key);
-}
-
-KERNEL k_merge_pairs(GroupInfo* info, const u32* __restrict__ best, const u32* __restrict__ edge_off, const u32* __restrict__ edge_dst, const u32* __restrict__ edge_w, u32 K,
-    const u32* __restrict__ min_size, const u64* __restrict__ claim, u32* parent, u32* merge_count)
-{
-	size_t gg = GTID;
-	if (gg >= K)
-		return;
-	u32 g = u32(gg);
-	u32 h = best[g];
-	if (h == NONE)
-		return;
-	u32 limit = *min_size * 2;
-	if (info[g].size > limit)
-		return;
-	u32 dst, src;
-	if (info[h].size <= limit)
-	{
-		// mover-mover: mutual picks only, handled once by the lower id
-		if (best[h] != g || h < g)
-			return;
-		dst = g;
-		src = h;
-	}
-	else
-	{
-		if (u32(~u32(claim[h])) != g)
-			return;
-		dst = h;
-		src = g;
-	}
-	u32 shared = 0;
-	for (u32 e = edge_off[dst]; e < edge_off[dst + 1]; ++e)
-		if (edge_dst[e] == src)
-			shared = edge_w[e];
-	GroupInfo a = info[dst], b = info[src];
-	a.size += b.size;
-	a.vertices += b.vertices;
-	a.vertices = a.vertices > shared ? a.vertices - shared : 1;
-	merge_bounds(a, b);
-	b.size = 0;
-	b.vertices = 0;
-	b.radius = 0;
-	info[dst] = a;
-	info[src] = b;
-	parent[src] = dst;
-	atomicAdd(merge_count, 1u);
-}
-
 KERNEL k_relabel_clusters(u32* label, const u32* __restrict__ parent, u32 K)
 {
 	size_t c = GTID;
@@ -341,11 +235,33 @@ KERNEL k_relabel_clusters(u32* label, const u32* __restrict__ parent, u32 K)
 	label[c] = parent[label[c]];
 }
 
-// ---- group-graph contraction by hashing (one merge round) ------------------------------------------------------------
-// Relabels every edge to the merged groups, drops self loops and combines parallel edges by inserting (src, dst) into an
-// open-addressed table that accumulates the shared-vertex weight. The first inserter of a key also counts the edge for
-// the CSR of its source. Rows of the rebuilt CSR are unordered; every consumer (k_pick_neighbor, k_merge_pairs) is
-// order independent, so the result is deterministic.
+// ---- merge rounds -----------------------------------------------------------------------------------------------------
+// Smallest-first agglomeration, bulk-synchronous: groups within 2x of the smallest open size are "movers" this round.
+// A mover merges with its pick when the pick is mutual (both movers; the lower id survives), or when the pick is a
+// larger, non-moving group that selected it as its best proposer (one proposer per group per round).
+//
+// The group graph is a flat, unordered list of directed edges (src, dst, shared-vertex weight), symmetric by construction.
+// Every step of a round is a reduction that does not depend on the order of that list: the pick is an atomicMax over
+// (score, ~neighbour id) keys, which is the order (score desc, min id asc, max id asc) of the edges of one group; the
+// contraction inserts the relabelled edges into an open-addressed table that sums the integer weights and then compacts
+// the table into the next list. So all rounds of a level run inside ONE persistent cooperative kernel, separated by grid
+// barriers, with no host round trip and no CSR rebuild.
+struct MergeArgs
+{
+	GroupInfo* info;
+	u32* label;
+	u32 *src[2], *dst[2], *w[2]; // edge lists, ping-pong
+	u64* table_key;
+	u32* table_w;
+	u64 *best_key, *claim;
+	u32 *best_w, *parent;
+	u32* state; // [0] edges in list 0 on entry, [1] edge counter of the next list, [2] smallest open size, [3] merges of the round, [4] rounds run
+	u32 K, target, max_size, max_rounds;
+	int use_bounds;
+};
+
+static const u64 EDGE_EMPTY = ~0ull;
+
 DEVFN u32 hash_edge(u64 key)
 {
 	key ^= key >> 33;
@@ -356,70 +272,326 @@ DEVFN u32 hash_edge(u64 key)
 	return u32(key);
 }
 
-KERNEL k_contract_insert(const u32* __restrict__ src, const u32* __restrict__ dst, const u32* __restrict__ w, const u32* __restrict__ parent, const u32* __restrict__ edge_count, u64 K, u64* table_key, u32* table_w, u32 mask,
-    u32* row_count, u32* new_edge_count)
+DEVFN bool pick_key_of_edge(const MergeArgs& a, int cur, u32 e, u32* g_out, u64* key_out)
 {
-	size_t e = GTID;
-	if (e >= *edge_count)
+	u32 g = a.src[cur][e], h = a.dst[cur][e];
+	const GroupInfo me = a.info[g];
+	if (me.size == 0 || me.size >= a.target)
+		return false;
+	const GroupInfo other = a.info[h];
+	if (other.size == 0 || other.size >= a.target)
+		return false;
+	if (me.size + other.size > a.max_size)
+		return false;
+	float score = g < h ? merge_score(me, other, a.w[cur][e], a.use_bounds != 0) : merge_score(other, me, a.w[cur][e], a.use_bounds != 0);
+	if (!(score > 0.f))
+		return false;
+	*g_out = g;
+	*key_out = (u64(__float_as_uint(score)) << 32) | u64(~h);
+	return true;
+}
+
+// B: best admissible neighbour of every open group
+DEVFN void mr_pick(const MergeArgs& a, int cur, u32 e)
+{
+	u32 g;
+	u64 key;
+	if (pick_key_of_edge(a, cur, e, &g, &key))
+		atomicMax(reinterpret_cast<unsigned long long*>(&a.best_key[g]), (unsigned long long)key);
+}
+
+// B2 (edges): the winning edge leaves its weight with the group
+DEVFN void mr_pick_weight(const MergeArgs& a, int cur, u32 e)
+{
+	u32 g;
+	u64 key;
+	if (pick_key_of_edge(a, cur, e, &g, &key) && a.best_key[g] == key)
+		a.best_w[g] = a.w[cur][e];
+}
+
+// C: movers propose to non-movers
+DEVFN void mr_propose(const MergeArgs& a, u32 g)
+{
+	u64 key = a.best_key[g];
+	if (key == 0)
 		return;
-	u64 s = parent[src[e]], d = parent[dst[e]];
+	u32 h = ~u32(key);
+	u32 limit = a.state[2] * 2;
+	if (a.info[g].size > limit || a.info[h].size <= limit)
+		return;
+	atomicMax(reinterpret_cast<unsigned long long*>(&a.claim[h]), (unsigned long long)((key & 0xffffffff00000000ull) | u64(~g)));
+}
+
+// D: merge
+DEVFN bool mr_merge(const MergeArgs& a, u32 g)
+{
+	u64 key = a.best_key[g];
+	if (key == 0)
+		return false;
+	u32 h = ~u32(key);
+	u32 limit = a.state[2] * 2;
+	if (a.info[g].size > limit)
+		return false;
+	u32 dst, src;
+	if (a.info[h].size <= limit)
+	{
+		// mover-mover: mutual picks only, handled once by the lower id
+		u64 hk = a.best_key[h];
+		if (hk == 0 || ~u32(hk) != g || h < g)
+			return false;
+		dst = g;
+		src = h;
+	}
+	else
+	{
+		if (u32(~u32(a.claim[h])) != g)
+			return false;
+		dst = h;
+		src = g;
+	}
+	u32 shared = a.best_w[g]; // weight of (g, h) == weight of (h, g)
+	GroupInfo x = a.info[dst], y = a.info[src];
+	x.size += y.size;
+	x.vertices += y.vertices;
+	x.vertices = x.vertices > shared ? x.vertices - shared : 1;
+	merge_bounds(x, y);
+	y.size = 0;
+	y.vertices = 0;
+	y.radius = 0;
+	a.info[dst] = x;
+	a.info[src] = y;
+	a.parent[src] = dst;
+	return true;
+}
+
+// E: relabel every edge to the merged groups, drop self loops, combine parallel edges in the table
+DEVFN void mr_contract_insert(const MergeArgs& a, int cur, u32 e, u32 mask)
+{
+	u64 s = a.parent[a.src[cur][e]], d = a.parent[a.dst[cur][e]];
 	if (s == d)
 		return;
-	u64 key = s * K + d;
+	u64 key = s * u64(a.K) + d;
 	u32 slot = hash_edge(key) & mask;
 	for (;;)
 	{
-		u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&table_key[slot]), ~0ull, (unsigned long long)key);
-		if (old == ~0ull)
-		{
-			atomicAdd(&row_count[s], 1u);
-			atomicAdd(new_edge_count, 1u);
-			break;
-		}
-		if (old == key)
+		u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&a.table_key[slot]), (unsigned long long)EDGE_EMPTY, (unsigned long long)key);
+		if (old == EDGE_EMPTY || old == key)
 			break;
 		slot = (slot + 1) & mask;
 	}
-	atomicAdd(&table_w[slot], w[e]);
+	atomicAdd(&a.table_w[slot], a.w[cur][e]);
 }
 
-KERNEL k_contract_fill(const u64* __restrict__ table_key, const u32* __restrict__ table_w, u32 table_size, u64 K, const u32* __restrict__ row_offset, u32* row_cursor, u32* src_out, u32* dst_out, u32* w_out)
+HOSTDEVFN u32 table_mask_for(u32 edges)
 {
-	size_t slot = GTID;
-	if (slot >= table_size)
-		return;
-	u64 key = table_key[slot];
-	if (key == ~0ull)
-		return;
-	u32 s = u32(key / K), d = u32(key % K);
-	u32 pos = row_offset[s] + atomicAdd(&row_cursor[s], 1u);
-	src_out[pos] = s;
-	dst_out[pos] = d;
-	w_out[pos] = table_w[slot];
+	u32 cap = 2;
+	while (cap < edges * 2)
+		cap <<= 1;
+	return cap - 1;
 }
 
-KERNEL k_relabel_edges(const u32* __restrict__ src, const u32* __restrict__ dst, const u32* __restrict__ parent, u32 E, u64 K, u64* edge_key, u32* keep)
+#ifdef CLODB_EMU
+KERNEL k_mr_pick(MergeArgs a, int cur, u32 n)
 {
-	size_t e = GTID;
-	if (e >= E)
+	if (GTID < n)
+		mr_pick(a, cur, u32(GTID));
+}
+KERNEL k_mr_pick_weight(MergeArgs a, int cur, u32 n)
+{
+	if (GTID < n)
+		mr_pick_weight(a, cur, u32(GTID));
+}
+KERNEL k_mr_min_size(MergeArgs a)
+{
+	u32 g = u32(GTID);
+	if (g < a.K && a.best_key[g] != 0)
+		atomicMin(&a.state[2], a.info[g].size);
+}
+KERNEL k_mr_propose(MergeArgs a)
+{
+	if (GTID < a.K)
+		mr_propose(a, u32(GTID));
+}
+KERNEL k_mr_merge(MergeArgs a)
+{
+	if (GTID < a.K && mr_merge(a, u32(GTID)))
+		a.state[3]++;
+}
+KERNEL k_mr_insert(MergeArgs a, int cur, u32 n, u32 mask)
+{
+	if (GTID < n)
+		mr_contract_insert(a, cur, u32(GTID), mask);
+}
+KERNEL k_mr_compact(MergeArgs a, int nxt, u32 cap)
+{
+	u32 slot = u32(GTID);
+	if (slot >= cap || a.table_key[slot] == EDGE_EMPTY)
 		return;
-	u64 s = parent[src[e]], d = parent[dst[e]];
-	edge_key[e] = s * K + d;
-	keep[e] = s != d ? 1u : 0u;
+	u32 pos = a.state[1]++;
+	a.src[nxt][pos] = u32(a.table_key[slot] / a.K);
+	a.dst[nxt][pos] = u32(a.table_key[slot] % a.K);
+	a.w[nxt][pos] = a.table_w[slot];
+	a.table_key[slot] = EDGE_EMPTY;
+	a.table_w[slot] = 0;
+}
+KERNEL k_mr_reset(MergeArgs a)
+{
+	u32 g = u32(GTID);
+	if (g >= a.K)
+		return;
+	a.label[g] = a.parent[a.label[g]];
+}
+KERNEL k_mr_reset2(MergeArgs a)
+{
+	u32 g = u32(GTID);
+	if (g >= a.K)
+		return;
+	a.best_key[g] = 0;
+	a.claim[g] = 0;
+	a.parent[g] = g;
 }
 
-KERNEL k_compact_edges(const u64* __restrict__ edge_key, const u32* __restrict__ w, const u32* __restrict__ keep_scanned, u32 total, u32 E, u64* key_out, u32* w_out)
+static void merge_rounds(MergeArgs a, u32 E)
 {
-	size_t e = GTID;
-	if (e >= E)
-		return;
-	u32 pos = keep_scanned[e];
-	u32 next = e + 1 < E ? keep_scanned[e + 1] : total;
-	if (next == pos)
-		return;
-	key_out[pos] = edge_key[e];
-	w_out[pos] = w[e];
+	int cur = 0;
+	u32 rounds = 0;
+	while (E > 0 && rounds < a.max_rounds)
+	{
+		rounds++;
+		a.state[2] = 0xffffffffu, a.state[3] = 0, a.state[1] = 0;
+		LAUNCH(k_mr_pick, E, a, cur, E);
+		LAUNCH(k_mr_pick_weight, E, a, cur, E);
+		LAUNCH(k_mr_min_size, a.K, a);
+		LAUNCH(k_mr_propose, a.K, a);
+		LAUNCH(k_mr_merge, a.K, a);
+		if (a.state[3] == 0)
+			break;
+		u32 mask = table_mask_for(E);
+		LAUNCH(k_mr_reset, a.K, a);
+		LAUNCH(k_mr_insert, E, a, cur, E, mask);
+		LAUNCH(k_mr_compact, size_t(mask) + 1, a, cur ^ 1, mask + 1);
+		LAUNCH(k_mr_reset2, a.K, a);
+		E = a.state[1];
+		cur ^= 1;
+	}
+	a.state[4] = rounds;
 }
+#else
+static const int MERGE_THREADS = 512;
+
+// append-compaction of a grid-stride loop: one atomicAdd per warp
+DEVFN u32 warp_append(bool take, u32* counter)
+{
+	unsigned mask = __ballot_sync(0xffffffffu, take);
+	if (!mask)
+		return 0;
+	u32 lane = threadIdx.x & 31;
+	int leader = __ffs(mask) - 1;
+	u32 off = 0;
+	if (int(lane) == leader)
+		off = atomicAdd(counter, u32(__popc(mask)));
+	off = __shfl_sync(0xffffffffu, off, leader);
+	return off + __popc(mask & ((1u << lane) - 1));
+}
+
+static __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_rounds(MergeArgs a)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const u32 gsize = gridDim.x * blockDim.x;
+	const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 E = *reinterpret_cast<volatile u32*>(a.state);
+	int cur = 0;
+	u32 rounds = 0;
+	while (E > 0 && rounds < a.max_rounds)
+	{
+		rounds++;
+		for (u32 e = gtid; e < E; e += gsize)
+			mr_pick(a, cur, e);
+		grid.sync();
+		if (gtid == 0)
+			a.state[1] = 0;
+		for (u32 e = gtid; e < E; e += gsize)
+			mr_pick_weight(a, cur, e);
+		for (u32 base = gtid - (gtid & 31); base < a.K; base += gsize)
+		{
+			u32 g = base + (gtid & 31);
+			u32 size = g < a.K && a.best_key[g] != 0 ? a.info[g].size : 0xffffffffu;
+			size = __reduce_min_sync(0xffffffffu, size);
+			if ((gtid & 31) == 0 && size != 0xffffffffu)
+				atomicMin(&a.state[2], size);
+		}
+		grid.sync();
+		for (u32 g = gtid; g < a.K; g += gsize)
+			mr_propose(a, g);
+		grid.sync();
+		for (u32 base = gtid - (gtid & 31); base < a.K; base += gsize)
+		{
+			u32 g = base + (gtid & 31);
+			bool merged = g < a.K && mr_merge(a, g);
+			unsigned m = __ballot_sync(0xffffffffu, merged);
+			if ((gtid & 31) == 0 && m)
+				atomicAdd(&a.state[3], u32(__popc(m)));
+		}
+		grid.sync();
+		if (*reinterpret_cast<volatile u32*>(a.state + 3) == 0)
+			break;
+		const u32 mask = table_mask_for(E);
+		for (u32 g = gtid; g < a.K; g += gsize)
+			a.label[g] = a.parent[a.label[g]];
+		for (u32 e = gtid; e < E; e += gsize)
+			mr_contract_insert(a, cur, e, mask);
+		grid.sync();
+		const int nxt = cur ^ 1;
+		for (u32 base = gtid - (gtid & 31); base <= mask; base += gsize)
+		{
+			u32 slot = base + (gtid & 31);
+			u64 key = a.table_key[slot];
+			bool take = key != EDGE_EMPTY;
+			u32 pos = warp_append(take, a.state + 1);
+			if (take)
+			{
+				a.src[nxt][pos] = u32(key / a.K);
+				a.dst[nxt][pos] = u32(key % a.K);
+				a.w[nxt][pos] = a.table_w[slot];
+				a.table_key[slot] = EDGE_EMPTY;
+				a.table_w[slot] = 0;
+			}
+		}
+		for (u32 g = gtid; g < a.K; g += gsize)
+		{
+			a.best_key[g] = 0;
+			a.claim[g] = 0;
+			a.parent[g] = g;
+		}
+		if (gtid == 0)
+		{
+			a.state[2] = 0xffffffffu;
+			a.state[3] = 0;
+		}
+		grid.sync();
+		E = *reinterpret_cast<volatile u32*>(a.state + 1);
+		cur = nxt;
+	}
+	if (gtid == 0)
+		a.state[4] = rounds;
+}
+
+static void merge_rounds(MergeArgs a, u32 E)
+{
+	static u32 max_blocks = 0;
+	if (!max_blocks)
+	{
+		int per_sm = 0, device = 0, sms = 0;
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, MERGE_THREADS, 0));
+		CUDA_CHECK(cudaGetDevice(&device));
+		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+		max_blocks = u32(std::max(1, per_sm) * sms);
+	}
+	size_t widest = std::max<size_t>(size_t(table_mask_for(E)) + 1, a.K);
+	u32 blocks = u32(std::min<size_t>(max_blocks, (widest + MERGE_THREADS - 1) / MERGE_THREADS));
+	LAUNCH_COOP(k_merge_rounds, blocks, MERGE_THREADS, a);
+}
+#endif
 
 // spatial merge of the leftover small groups along the Morton order of their centres (replaces mergeSpatial's kd-tree
 // leaves, partition.cpp:368-480): each still-open group looks at its nearest open neighbours in that order
@@ -777,7 +949,6 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 	u32* e_src = nullptr;
 	u32* e_dst = nullptr;
 	u32* e_w = nullptr;
-	u32* e_off = temp.alloc<u32>(size_t(K) + 1);
 	u64* e_key = nullptr;
 	u64* e_key_tmp = nullptr;
 	u32* e_val = nullptr;
@@ -811,64 +982,33 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 		E = dev_read(scalars);
 		LAUNCH(k_edge_combine, E0, e_key, nullptr, e_flag, E, E0, u64(K), e_src, e_dst, e_w);
 	}
-	auto rebuild_offsets = [&]() {
-		dev_memset(e_off, 0, (size_t(K) + 1) * sizeof(u32));
-		LAUNCH(k_edge_src_count, E, e_src, E, e_off);
-		exclusive_scan_u32(e_off, e_off, size_t(K) + 1, nullptr, temp);
-	};
-	rebuild_offsets();
-
-	// ---- merge rounds
-	// scalars: [1] merges this round, [3] smallest open size, [8] current edge count, [9] next edge count
-	u32 rounds = 0;
+	// ---- merge rounds: one persistent kernel, no host round trip (state: see MergeArgs)
 	if (E > 0)
 	{
-		size_t table_cap = 1;
+		size_t table_cap = 2;
 		while (table_cap < size_t(E) * 2)
 			table_cap <<= 1;
-		u64* table_key = temp.alloc<u64>(table_cap);
-		u32* table_w = temp.alloc<u32>(table_cap);
-		u32* e_src_alt = temp.alloc<u32>(E);
-		u32* e_dst_alt = temp.alloc<u32>(E);
-		u32* e_w_alt = temp.alloc<u32>(E);
-		u32* row_cursor = temp.alloc<u32>(K);
-		dev_h2d(scalars + 8, &E, sizeof(u32));
-		u32 E_cur = E;
-		for (;;)
-		{
-			rounds++;
-			dev_memset(scalars + 3, 0xff, sizeof(u32));
-			LAUNCH(k_pick_neighbor, K, info, e_off, e_dst, e_w, K, target, max_size, config.partition_spatial ? 1 : 0, best, best_score, scalars + 3);
-			iota(parent, K);
-			dev_memset(scalars + 1, 0, sizeof(u32));
-			dev_memset(claim, 0, size_t(K) * sizeof(u64));
-			LAUNCH(k_propose, K, info, best, best_score, K, scalars + 3, claim);
-			LAUNCH(k_merge_pairs, K, info, best, e_off, e_dst, e_w, K, scalars + 3, claim, parent, scalars + 1);
-			u32 merged = dev_read(scalars + 1);
-			if (merged == 0 || rounds > 4096)
-				break;
-			LAUNCH(k_relabel_clusters, K, label, parent, K);
-			// contract the group graph
-			size_t cap = 1;
-			while (cap < size_t(E_cur) * 2)
-				cap <<= 1;
-			dev_memset(table_key, 0xff, cap * sizeof(u64));
-			dev_memset(table_w, 0, cap * sizeof(u32));
-			dev_memset(e_off, 0, (size_t(K) + 1) * sizeof(u32));
-			dev_memset(row_cursor, 0, size_t(K) * sizeof(u32));
-			dev_memset(scalars + 9, 0, sizeof(u32));
-			LAUNCH(k_contract_insert, E_cur, e_src, e_dst, e_w, parent, scalars + 8, u64(K), table_key, table_w, u32(cap - 1), e_off, scalars + 9);
-			exclusive_scan_u32(e_off, e_off, size_t(K) + 1, nullptr, temp);
-			LAUNCH(k_contract_fill, cap, table_key, table_w, u32(cap), u64(K), e_off, row_cursor, e_src_alt, e_dst_alt, e_w_alt);
-			dev_d2d(scalars + 8, scalars + 9, sizeof(u32));
-			std::swap(e_src, e_src_alt);
-			std::swap(e_dst, e_dst_alt);
-			std::swap(e_w, e_w_alt);
-			// every merge removes at least the two directed edges between the merged pair
-			E_cur = E_cur > 2 * merged ? E_cur - 2 * merged : 0;
-			if (E_cur == 0)
-				break;
-		}
+		MergeArgs ma;
+		ma.info = info, ma.label = label;
+		ma.src[0] = e_src, ma.dst[0] = e_dst, ma.w[0] = e_w;
+		ma.src[1] = temp.alloc<u32>(E), ma.dst[1] = temp.alloc<u32>(E), ma.w[1] = temp.alloc<u32>(E);
+		ma.table_key = temp.alloc<u64>(table_cap);
+		ma.table_w = temp.alloc<u32>(table_cap);
+		ma.best_key = temp.alloc<u64>(K);
+		ma.claim = claim;
+		ma.best_w = best;
+		ma.parent = parent;
+		ma.state = scalars + 8;
+		ma.K = K, ma.target = target, ma.max_size = max_size, ma.max_rounds = 4096;
+		ma.use_bounds = config.partition_spatial ? 1 : 0;
+		dev_memset(ma.table_key, 0xff, table_cap * sizeof(u64));
+		dev_memset(ma.table_w, 0, table_cap * sizeof(u32));
+		dev_memset(ma.best_key, 0, size_t(K) * sizeof(u64));
+		dev_memset(claim, 0, size_t(K) * sizeof(u64));
+		iota(parent, K);
+		u32 st[5] = {E, 0, 0xffffffffu, 0, 0};
+		dev_h2d(ma.state, st, sizeof(st));
+		merge_rounds(ma, E);
 	}
 
 	// ---- leftovers: spatially merge open groups (only when positions are used, partition.cpp:599-611)
@@ -966,7 +1106,7 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 
 	out.group_count = G_final;
 	out.group_cluster_offset_host = dev_download(out.group_cluster_offset, size_t(G_final) + 1);
-	out.merge_rounds = rounds;
+	out.merge_rounds = 0;
 	return out;
 }
 
