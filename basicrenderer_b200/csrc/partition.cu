@@ -83,6 +83,104 @@ KERNEL k_cluster_unique(const u32* __restrict__ tri, const u32* __restrict__ clu
 	center_radius[c * 4 + 3] = sqrtf(r2);
 }
 
+#ifndef CLODB_EMU
+// Warp-cooperative k_cluster_unique (same results): one warp per cluster. The remapped corner ids go through a shared-memory
+// hash table that keeps the smallest corner position per vertex, so the first-occurrence order of the serial loop is
+// recovered with a ballot; the centre is summed in that order (three lanes, one coordinate each) to keep its bits.
+static const int CU_WARPS = 4;
+static __global__ void __launch_bounds__(CU_WARPS * 32) k_cluster_unique_warp(const u32* __restrict__ tri, const u32* __restrict__ cluster_tri_offset, const u32* __restrict__ remap, const float* __restrict__ positions, u32 K, u32 stride,
+    u32* cv, u32* cv_count, float* center_radius)
+{
+	__shared__ u32 s_key[CU_WARPS][512];
+	__shared__ u32 s_pos[CU_WARPS][512];
+	__shared__ float s_xyz[CU_WARPS][3][128];
+	__shared__ float s_centre[CU_WARPS][3];
+	const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 c = blockIdx.x * CU_WARPS + w;
+	if (c >= K)
+		return;
+	u32* key = s_key[w];
+	u32* pos = s_pos[w];
+	for (u32 i = lane; i < 512; i += 32)
+		key[i] = NONE, pos[i] = NONE;
+	__syncwarp();
+	const u32 begin = cluster_tri_offset[c] * 3, n = cluster_tri_offset[c + 1] * 3 - begin;
+	const u32 cap = stride < 128 ? stride : 128;
+	for (u32 j = lane; j < n; j += 32)
+	{
+		u32 v = remap[tri[begin + j]];
+		u32 h = (v * 0x9E3779B1u) >> 23;
+		for (;;)
+		{
+			u32 old = atomicCAS(&key[h], NONE, v);
+			if (old == NONE || old == v)
+				break;
+			h = (h + 1) & 511;
+		}
+		atomicMin(&pos[h], j);
+	}
+	__syncwarp();
+	u32 count = 0;
+	for (u32 base = 0; base < n; base += 32)
+	{
+		u32 j = base + lane;
+		bool first = false;
+		u32 v = 0;
+		if (j < n)
+		{
+			v = remap[tri[begin + j]];
+			u32 h = (v * 0x9E3779B1u) >> 23;
+			while (key[h] != v)
+				h = (h + 1) & 511;
+			first = pos[h] == j;
+		}
+		unsigned mask = __ballot_sync(0xffffffffu, first);
+		u32 rank = count + __popc(mask & ((1u << lane) - 1));
+		if (first && rank < cap)
+		{
+			cv[size_t(c) * stride + rank] = v;
+			s_xyz[w][0][rank] = positions[size_t(v) * 3 + 0];
+			s_xyz[w][1][rank] = positions[size_t(v) * 3 + 1];
+			s_xyz[w][2][rank] = positions[size_t(v) * 3 + 2];
+		}
+		count += __popc(mask);
+	}
+	count = count < cap ? count : cap;
+	__syncwarp();
+	if (lane < 3)
+	{
+		float sum = 0;
+		for (u32 j = 0; j < count; ++j)
+			sum += s_xyz[w][lane][j];
+		if (count)
+			sum /= float(count);
+		s_centre[w][lane] = sum;
+	}
+	__syncwarp();
+	float cx = s_centre[w][0], cy = s_centre[w][1], cz = s_centre[w][2];
+	float r2 = 0;
+	for (u32 j = lane; j < count; j += 32)
+	{
+		float px = s_xyz[w][0][j], py = s_xyz[w][1][j], pz = s_xyz[w][2][j];
+		float d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy) + (pz - cz) * (pz - cz);
+		r2 = r2 < d2 ? d2 : r2;
+	}
+	for (int d = 16; d >= 1; d >>= 1)
+	{
+		float o = __shfl_xor_sync(0xffffffffu, r2, d);
+		r2 = r2 < o ? o : r2;
+	}
+	if (lane == 0)
+	{
+		cv_count[c] = count;
+		center_radius[c * 4 + 0] = cx;
+		center_radius[c * 4 + 1] = cy;
+		center_radius[c * 4 + 2] = cz;
+		center_radius[c * 4 + 3] = sqrtf(r2);
+	}
+}
+#endif
+
 KERNEL k_emit_vertex_pairs(const u32* __restrict__ cv, const u32* __restrict__ cv_count, const u32* __restrict__ cv_offset, u32 K, u32 stride, u32* pair_vertex, u32* pair_cluster)
 {
 	size_t c = GTID;
@@ -788,39 +886,10 @@ KERNEL k_apply_part_remap(u32* part, const u32* __restrict__ part_remap, u32* cl
 
 // refined-id cap (clusterlod.h:432-507): bucket a group's clusters by refined id in first-seen order; if there are more than
 // `cap` buckets, emit the buckets back to back, starting a new group every `cap` buckets
-KERNEL k_refined_cap(const u32* __restrict__ group_offset, u32* group_clusters, const int* __restrict__ cluster_refined, u32 G, u32 cap, u32* scratch_clusters, u32* split_marks, u32* extra_groups)
+// slow path of the refined-id cap (clusterlod.h:432-507): bucket order by first occurrence, clusters keep their relative
+// order inside a bucket, a new group starts after every `cap` buckets
+DEVFN void refined_cap_split(u32 begin, u32 n, u32* group_clusters, const int* __restrict__ cluster_refined, u32 cap, u32* scratch_clusters, u32* split_marks, u32* extra_groups)
 {
-	size_t g = GTID;
-	if (g >= G)
-		return;
-	u32 begin = group_offset[g], end = group_offset[g + 1];
-	u32 n = end - begin;
-	// first-seen refined keys; groups hold at most a few hundred clusters
-	int keys[64];
-	u32 nkeys = 0;
-	bool overflow = false;
-	for (u32 j = 0; j < n && !overflow; ++j)
-	{
-		int r = cluster_refined[group_clusters[begin + j]];
-		bool seen = false;
-		for (u32 k = 0; k < nkeys; ++k)
-			if (keys[k] == r)
-			{
-				seen = true;
-				break;
-			}
-		if (!seen)
-		{
-			if (nkeys == 64)
-				overflow = true;
-			else
-				keys[nkeys++] = r;
-		}
-	}
-	if (!overflow && nkeys <= cap)
-		return;
-
-	// slow path: bucket order by first occurrence, clusters keep their relative order inside a bucket
 	u32 out = begin;
 	u32 buckets_in_current = 0;
 	u32 extra = 0;
@@ -852,6 +921,78 @@ KERNEL k_refined_cap(const u32* __restrict__ group_offset, u32* group_clusters, 
 	if (extra)
 		atomicAdd(extra_groups, extra);
 }
+
+KERNEL k_refined_cap(const u32* __restrict__ group_offset, u32* group_clusters, const int* __restrict__ cluster_refined, u32 G, u32 cap, u32* scratch_clusters, u32* split_marks, u32* extra_groups)
+{
+	size_t g = GTID;
+	if (g >= G)
+		return;
+	u32 begin = group_offset[g], end = group_offset[g + 1];
+	u32 n = end - begin;
+	// first-seen refined keys; groups hold at most a few hundred clusters
+	int keys[64];
+	u32 nkeys = 0;
+	bool overflow = false;
+	for (u32 j = 0; j < n && !overflow; ++j)
+	{
+		int r = cluster_refined[group_clusters[begin + j]];
+		bool seen = false;
+		for (u32 k = 0; k < nkeys; ++k)
+			if (keys[k] == r)
+			{
+				seen = true;
+				break;
+			}
+		if (!seen)
+		{
+			if (nkeys == 64)
+				overflow = true;
+			else
+				keys[nkeys++] = r;
+		}
+	}
+	if (!overflow && nkeys <= cap)
+		return;
+	refined_cap_split(begin, n, group_clusters, cluster_refined, cap, scratch_clusters, split_marks, extra_groups);
+}
+
+#ifndef CLODB_EMU
+// One warp per group: the distinct refined ids are counted 32 clusters at a time (match_any de-duplicates a chunk, chunk
+// leaders are checked against the ids seen so far); only groups above the cap take the serial split.
+static __global__ void __launch_bounds__(256) k_refined_cap_warp(const u32* __restrict__ group_offset, u32* group_clusters, const int* __restrict__ cluster_refined, u32 G, u32 cap, u32* scratch_clusters, u32* split_marks, u32* extra_groups)
+{
+	__shared__ int s_keys[8][64];
+	const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 g = blockIdx.x * 8 + w;
+	if (g >= G)
+		return;
+	const u32 begin = group_offset[g], n = group_offset[g + 1] - begin;
+	const u32 limit = cap < 63 ? cap : 63;
+	u32 nkeys = 0;
+	for (u32 base = 0; base < n && nkeys <= limit; base += 32)
+	{
+		u32 j = base + lane;
+		bool valid = j < n;
+		int r = valid ? cluster_refined[group_clusters[begin + j]] : 0;
+		unsigned peers = __match_any_sync(0xffffffffu, u32(r)) & __ballot_sync(0xffffffffu, valid);
+		bool leader = valid && (__ffs(peers) - 1 == int(lane));
+		bool seen = false;
+		for (u32 k = 0; k < nkeys; ++k)
+			seen |= s_keys[w][k] == r;
+		bool fresh = leader && !seen;
+		unsigned mask = __ballot_sync(0xffffffffu, fresh);
+		u32 slot = nkeys + __popc(mask & ((1u << lane) - 1));
+		if (fresh && slot < 64)
+			s_keys[w][slot] = r;
+		nkeys += __popc(mask);
+		__syncwarp();
+	}
+	if (nkeys <= cap)
+		return;
+	if (lane == 0)
+		refined_cap_split(begin, n, group_clusters, cluster_refined, cap, scratch_clusters, split_marks, extra_groups);
+}
+#endif
 
 KERNEL k_group_start_flags(const u32* __restrict__ group_offset, u32 G, u32* split_marks)
 {
@@ -932,7 +1073,14 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 	u32* cv_count = temp.alloc<u32>(size_t(K) + 1);
 	u32* cv_offset = temp.alloc<u32>(size_t(K) + 1);
 	float* center_radius = temp.alloc<float>(size_t(K) * 4);
+#ifdef CLODB_EMU
 	LAUNCH(k_cluster_unique, K, tri, cluster_tri_offset, remap, positions, K, stride, cv, cv_count, center_radius);
+#else
+	if (stride <= 128 && config.max_triangles * 3 <= 384)
+		LAUNCH_GRID(k_cluster_unique_warp, (K + CU_WARPS - 1) / CU_WARPS, CU_WARPS * 32, tri, cluster_tri_offset, remap, positions, K, stride, cv, cv_count, center_radius);
+	else
+		LAUNCH(k_cluster_unique, K, tri, cluster_tri_offset, remap, positions, K, stride, cv, cv_count, center_radius);
+#endif
 	exclusive_scan_u32(cv_count, cv_offset, K, scalars, temp);
 	u32 P = dev_read(scalars);
 
@@ -1096,7 +1244,11 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 	if (cap > 0)
 	{
 		u32* scratch_clusters = temp.alloc<u32>(K);
+#ifdef CLODB_EMU
 		LAUNCH(k_refined_cap, G, group_offset, out.group_clusters, cluster_refined, G, cap, scratch_clusters, marks, scalars + 2);
+#else
+		LAUNCH_GRID(k_refined_cap_warp, (G + 7) / 8, 256, group_offset, out.group_clusters, cluster_refined, G, cap, scratch_clusters, marks, scalars + 2);
+#endif
 	}
 	LAUNCH(k_group_start_flags, G, group_offset, G, marks);
 	u32* marks_scanned = temp.alloc<u32>(size_t(K) + 1);
