@@ -485,29 +485,6 @@ static const int SA_THREADS = CLODB_SA_THREADS;
 static const int SA_ITEMS = CLODB_SA_ITEMS;
 static const int SA_TILE = SA_THREADS * SA_ITEMS;
 
-DEVFN ScanElem load_elem(const Box* boxes, const u32* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, u32 T, u32 j, bool backward)
-{
-	if (j >= T)
-		return scan_identity();
-	u32 p = backward ? T - 1 - j : j;
-	u32 n = node_of_pos[p];
-	if (n == NODE_DONE)
-	{
-		// finished nodes are never read by the pivot search: no box gather, and the scan restarts here
-		ScanElem done = scan_identity();
-		done.flag = 1;
-		return done;
-	}
-	ScanElem e;
-	// the 32-byte box is gathered with two 16-byte loads (one sector) instead of six scalar ones
-	const float4* bp = reinterpret_cast<const float4*>(boxes + order[p]);
-	float4 lo = __ldg(bp), hi = __ldg(bp + 1);
-	e.mn[0] = lo.x, e.mn[1] = lo.y, e.mn[2] = lo.z;
-	e.mx[0] = hi.x, e.mx[1] = hi.y, e.mx[2] = hi.z;
-	e.flag = backward ? p == node_begin[n] + node_count[n] - 1 : p == node_begin[n];
-	return e;
-}
-
 // inclusive block scan of per-thread aggregates; returns the exclusive prefix for this thread; total via smem
 DEVFN ScanElem block_scan_exclusive(const ScanElem& agg, ScanElem* smem /* 8 */, ScanElem* block_total)
 {
@@ -564,26 +541,102 @@ struct SweepArgs
 	float* area; // 6 arrays of T + 1 floats: [axis * 2 + backward]
 };
 
+// One thread owns the 8 consecutive positions [q, q + 8) of a sweep, q a multiple of 8 (the backward sweep counts from the
+// padded end, so its chunks are aligned too). Everything a chunk needs is requested before anything is consumed: two
+// 16-byte loads of the node ids, two of the order entries, one neighbouring node id, then all box gathers (two 16-byte
+// loads = one sector each) are in flight together. Segment heads come from comparing neighbouring node ids (a node is a
+// contiguous run of positions with a unique id), so the node tables are not touched.
+template <bool BACK>
+DEVFN void sa_load_chunk(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, u32 T, long q, ScanElem (&e)[SA_ITEMS])
+{
+	static_assert(SA_ITEMS == 8, "chunk layout");
+	u32 n[8], o[8];
+	u32 edge = NODE_DONE; // node id just outside the chunk on the side the sweep comes from
+	bool has_edge = false;
+	if (q >= 0 && q + 8 <= long(T))
+	{
+		const uint4* np = reinterpret_cast<const uint4*>(node_of_pos + q);
+		const uint4* op = reinterpret_cast<const uint4*>(order + q);
+		uint4 n0 = __ldg(np), n1 = __ldg(np + 1), o0 = __ldg(op), o1 = __ldg(op + 1);
+		n[0] = n0.x, n[1] = n0.y, n[2] = n0.z, n[3] = n0.w, n[4] = n1.x, n[5] = n1.y, n[6] = n1.z, n[7] = n1.w;
+		o[0] = o0.x, o[1] = o0.y, o[2] = o0.z, o[3] = o0.w, o[4] = o1.x, o[5] = o1.y, o[6] = o1.z, o[7] = o1.w;
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+		{
+			long p = q + i;
+			bool in = p >= 0 && p < long(T);
+			n[i] = in ? __ldg(node_of_pos + p) : NODE_DONE;
+			o[i] = in ? __ldg(order + p) : 0u;
+		}
+	}
+	long pe = BACK ? q + 8 : q - 1;
+	if (pe >= 0 && pe < long(T))
+	{
+		edge = __ldg(node_of_pos + pe);
+		has_edge = true;
+	}
+	float4 lo[8], hi[8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i)
+		if (n[i] != NODE_DONE)
+		{
+			const float4* bp = reinterpret_cast<const float4*>(boxes + o[i]);
+			lo[i] = __ldg(bp), hi[i] = __ldg(bp + 1);
+		}
+#pragma unroll
+	for (int k = 0; k < 8; ++k)
+	{
+		const int i = BACK ? 7 - k : k; // position inside the chunk of the k-th element in scan order
+		long p = q + i;
+		ScanElem x = scan_identity();
+		if (p >= 0 && p < long(T))
+		{
+			if (n[i] == NODE_DONE)
+				x.flag = 1; // finished nodes are never read by the pivot search: no box gather, and the scan restarts here
+			else
+			{
+				x.mn[0] = lo[i].x, x.mn[1] = lo[i].y, x.mn[2] = lo[i].z;
+				x.mx[0] = hi[i].x, x.mx[1] = hi[i].y, x.mx[2] = hi[i].z;
+				// the element the sweep visited just before this one
+				const int ip = BACK ? i + 1 : i - 1;
+				bool head;
+				if (ip < 0 || ip > 7)
+					head = !has_edge || edge != n[i];
+				else
+					head = (BACK && p + 1 >= long(T)) || n[ip] != n[i];
+				x.flag = head ? 1u : 0u;
+			}
+		}
+		e[k] = x;
+	}
+}
+
 // All six sweeps of a tree level (3 axis orders x forward/backward) in one launch: blockIdx.x = tile * 6 + sweep, so the six
 // independent tile chains advance concurrently and hide each other's look-back latency.
-static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __restrict__ boxes, SweepArgs sw, const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count,
+static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __restrict__ boxes, SweepArgs sw, const u32* __restrict__ node_of_pos,
     u32 T, u32 tiles, u32* chain_flags, char* chain_aggregate, char* chain_inclusive, u32 epoch)
 {
 	__shared__ ScanElem smem[SA_THREADS / 32];
 	__shared__ ScanElem s_prefix;
 	const u32 sweep = blockIdx.x % 6, tile = blockIdx.x / 6;
-	const int backward = sweep & 1;
+	const bool backward = (sweep & 1) != 0;
 	const u32* __restrict__ order = sw.order[sweep >> 1];
 	float* out_area = sw.area + size_t(sweep) * (size_t(T) + 1);
-	u32 base = tile * SA_TILE + threadIdx.x * SA_ITEMS;
+	const u32 base = tile * SA_TILE + threadIdx.x * SA_ITEMS;
+	const u32 Tpad = (T + 7u) & ~7u;
+	const long q = backward ? long(Tpad) - 8 - long(base) : long(base);
 	ScanElem e[SA_ITEMS];
+	if (backward)
+		sa_load_chunk<true>(boxes, order, node_of_pos, T, q, e);
+	else
+		sa_load_chunk<false>(boxes, order, node_of_pos, T, q, e);
 	ScanElem agg = scan_identity();
 #pragma unroll
 	for (int k = 0; k < SA_ITEMS; ++k)
-	{
-		e[k] = load_elem(boxes, order, node_of_pos, node_begin, node_count, T, base + k, backward != 0);
 		agg = scan_combine(agg, e[k]);
-	}
 	ScanElem total;
 	ScanElem ex = block_scan_exclusive(agg, smem, &total);
 	if (threadIdx.x < 32)
@@ -599,10 +652,9 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 	for (int k = 0; k < SA_ITEMS; ++k)
 	{
 		prefix = scan_combine(prefix, e[k]);
-		u32 j = base + k;
-		if (j < T)
+		long p = q + (backward ? 7 - k : k);
+		if (p >= 0 && p < long(T))
 		{
-			u32 p = backward ? T - 1 - j : j;
 			float sx = prefix.mx[0] - prefix.mn[0], sy = prefix.mx[1] - prefix.mn[1], sz = prefix.mx[2] - prefix.mn[2];
 			out_area[p] = (sx * sy + sy * sz) + sz * sx;
 		}
@@ -612,14 +664,14 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 // areas: 6 arrays of T + 1 floats, [axis * 2 + backward]
 static void seg_area_scan_all(const Box* boxes, u32* const* order, const u32* node_of_pos, const u32* node_begin, const u32* node_count, float* areas, u32 T, Arena&)
 {
-	u32 tiles = (T + SA_TILE - 1) / SA_TILE;
+	u32 tiles = (((T + 7u) & ~7u) + SA_TILE - 1) / SA_TILE;
 	scan_chain_reserve(size_t(tiles) * 6);
 	u32 epoch = scan_chain_next_epoch();
 	SweepArgs sw;
 	for (int k = 0; k < 3; ++k)
 		sw.order[k] = order[k];
 	sw.area = areas;
-	LAUNCH_GRID(k_sa_chained, size_t(tiles) * 6, SA_THREADS, boxes, sw, node_of_pos, node_begin, node_count, T, tiles, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch);
+	LAUNCH_GRID(k_sa_chained, size_t(tiles) * 6, SA_THREADS, boxes, sw, node_of_pos, T, tiles, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch);
 }
 #endif
 
