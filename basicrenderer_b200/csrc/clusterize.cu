@@ -475,6 +475,30 @@ DEVFN ScanElem scan_shfl_up(const ScanElem& e, int d)
 	return r;
 }
 
+DEVFN ScanElem scan_shfl_down(const ScanElem& e, int d)
+{
+	ScanElem r;
+	for (int k = 0; k < 3; ++k)
+	{
+		r.mn[k] = __shfl_down_sync(0xffffffffu, e.mn[k], d);
+		r.mx[k] = __shfl_down_sync(0xffffffffu, e.mx[k], d);
+	}
+	r.flag = 0;
+	return r;
+}
+
+DEVFN ScanElem scan_shfl_idx(const ScanElem& e, int src)
+{
+	ScanElem r;
+	for (int k = 0; k < 3; ++k)
+	{
+		r.mn[k] = __shfl_sync(0xffffffffu, e.mn[k], src);
+		r.mx[k] = __shfl_sync(0xffffffffu, e.mx[k], src);
+	}
+	r.flag = 0;
+	return r;
+}
+
 #ifndef CLODB_SA_THREADS
 #define CLODB_SA_THREADS 256
 #endif
@@ -533,6 +557,83 @@ struct OpSegBox
 	}
 };
 
+// ---- look-back over packed box descriptors --------------------------------------------------------------------------
+// A tile's aggregate (or inclusive prefix) is published as two self-validating 16-byte words {tag, min xyz} {tag, max xyz}:
+// each word is written and read with one aligned 16-byte access, a reader accepts a descriptor when both tags agree, so
+// there is no fence and a look-back window costs one L2 round trip (prims.cuh explains the bound). The segment flag does
+// not travel: an aggregate with a head inside is published as an inclusive prefix, and the flag of the left-most operand
+// of a combination is never inspected.
+DEVFN void sa_desc_store(char* desc, u32 tile, u32 tag, const ScanElem& v)
+{
+	char* p = desc + size_t(tile) * 32;
+	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(tag), "r"(__float_as_uint(v.mn[0])), "r"(__float_as_uint(v.mn[1])), "r"(__float_as_uint(v.mn[2])) : "memory");
+	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 16), "r"(tag), "r"(__float_as_uint(v.mx[0])), "r"(__float_as_uint(v.mx[1])), "r"(__float_as_uint(v.mx[2])) : "memory");
+}
+
+// returns the tag when both words carry the same one, 0 otherwise
+DEVFN u32 sa_desc_load(const char* desc, u32 tile, ScanElem& v)
+{
+	const char* p = desc + size_t(tile) * 32;
+	u32 t0, t1, a0, a1, a2, b0, b1, b2;
+	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(a0), "=r"(a1), "=r"(a2) : "l"(p) : "memory");
+	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t1), "=r"(b0), "=r"(b1), "=r"(b2) : "l"(p + 16) : "memory");
+	v.mn[0] = __uint_as_float(a0), v.mn[1] = __uint_as_float(a1), v.mn[2] = __uint_as_float(a2);
+	v.mx[0] = __uint_as_float(b0), v.mx[1] = __uint_as_float(b1), v.mx[2] = __uint_as_float(b2);
+	v.flag = 0;
+	return t0 == t1 ? t0 : 0u;
+}
+
+// Called by all 32 lanes of warp 0 with the tile's aggregate; returns the tile's exclusive prefix (valid in every lane)
+DEVFN ScanElem sa_lookback(u32 tile, const ScanElem& tile_aggregate, char* desc, u32 epoch)
+{
+	const int lane = threadIdx.x & 31;
+	const u32 tag_agg = (epoch << 2) | 1u, tag_inc = (epoch << 2) | 2u;
+	if (tile == 0)
+	{
+		if (lane == 0)
+			sa_desc_store(desc, 0, tag_inc, tile_aggregate);
+		return scan_identity();
+	}
+	const bool independent = tile_aggregate.flag != 0;
+	if (lane == 0)
+		sa_desc_store(desc, tile, independent ? tag_inc : tag_agg, tile_aggregate);
+	ScanElem prefix = scan_identity();
+	int p = int(tile) - 1;
+	for (;;)
+	{
+		int idx = p - lane;
+		ScanElem v = scan_identity();
+		u32 t = tag_inc;
+		for (;;)
+		{
+			if (idx >= 0)
+				t = sa_desc_load(desc, u32(idx), v);
+			if (__all_sync(0xffffffffu, t == tag_agg || t == tag_inc))
+				break;
+		}
+		unsigned inc_mask = __ballot_sync(0xffffffffu, t == tag_inc);
+		int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32; // nearest predecessor whose inclusive prefix is known (lanes past the start count)
+		if (idx < 0 || lane > first_inc)
+			v = scan_identity();
+		// ordered reduction: lane L is farther back than lane L-1, so it is the left operand
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			ScanElem o = scan_shfl_down(v, d);
+			if (lane + d < 32)
+				v = scan_combine(o, v);
+		}
+		v = scan_shfl_idx(v, 0);
+		prefix = scan_combine(v, prefix);
+		if (inc_mask)
+			break;
+		p -= 32;
+	}
+	if (lane == 0 && !independent)
+		sa_desc_store(desc, tile, tag_inc, scan_combine(prefix, tile_aggregate));
+	return prefix;
+}
+
 // Segmented inclusive min/max scan of the triangle boxes along one axis order -> surface area at every position, in one
 // chained pass (prims.cuh): per element it reads order u32 + node id u32 + the gathered 32-byte box and writes one f32.
 struct SweepArgs
@@ -541,7 +642,7 @@ struct SweepArgs
 	float* area; // 6 arrays of T + 1 floats: [axis * 2 + backward]
 };
 
-// One thread owns the 8 consecutive positions [q, q + 8) of a sweep, q a multiple of 8 (the backward sweep counts from the
+// One thread owns the SA_ITEMS consecutive positions [q, q + SA_ITEMS) of a sweep, q a multiple of SA_ITEMS (the backward sweep counts from the
 // padded end, so its chunks are aligned too). Everything a chunk needs is requested before anything is consumed: two
 // 16-byte loads of the node ids, two of the order entries, one neighbouring node id, then all box gathers (two 16-byte
 // loads = one sector each) are in flight together. Segment heads come from comparing neighbouring node ids (a node is a
@@ -549,22 +650,27 @@ struct SweepArgs
 template <bool BACK>
 DEVFN void sa_load_chunk(const Box* __restrict__ boxes, const u32* __restrict__ order, const u32* __restrict__ node_of_pos, u32 T, long q, ScanElem (&e)[SA_ITEMS])
 {
-	static_assert(SA_ITEMS == 8, "chunk layout");
-	u32 n[8], o[8];
+	static_assert(SA_ITEMS == 8 || SA_ITEMS == 4, "chunk layout");
+	const int N = SA_ITEMS;
+	u32 n[N], o[N];
 	u32 edge = NODE_DONE; // node id just outside the chunk on the side the sweep comes from
 	bool has_edge = false;
-	if (q >= 0 && q + 8 <= long(T))
+	if (q >= 0 && q + N <= long(T))
 	{
 		const uint4* np = reinterpret_cast<const uint4*>(node_of_pos + q);
 		const uint4* op = reinterpret_cast<const uint4*>(order + q);
-		uint4 n0 = __ldg(np), n1 = __ldg(np + 1), o0 = __ldg(op), o1 = __ldg(op + 1);
-		n[0] = n0.x, n[1] = n0.y, n[2] = n0.z, n[3] = n0.w, n[4] = n1.x, n[5] = n1.y, n[6] = n1.z, n[7] = n1.w;
-		o[0] = o0.x, o[1] = o0.y, o[2] = o0.z, o[3] = o0.w, o[4] = o1.x, o[5] = o1.y, o[6] = o1.z, o[7] = o1.w;
+#pragma unroll
+		for (int v = 0; v < N / 4; ++v)
+		{
+			uint4 nv = __ldg(np + v), ov = __ldg(op + v);
+			n[v * 4 + 0] = nv.x, n[v * 4 + 1] = nv.y, n[v * 4 + 2] = nv.z, n[v * 4 + 3] = nv.w;
+			o[v * 4 + 0] = ov.x, o[v * 4 + 1] = ov.y, o[v * 4 + 2] = ov.z, o[v * 4 + 3] = ov.w;
+		}
 	}
 	else
 	{
 #pragma unroll
-		for (int i = 0; i < 8; ++i)
+		for (int i = 0; i < N; ++i)
 		{
 			long p = q + i;
 			bool in = p >= 0 && p < long(T);
@@ -572,24 +678,24 @@ DEVFN void sa_load_chunk(const Box* __restrict__ boxes, const u32* __restrict__ 
 			o[i] = in ? __ldg(order + p) : 0u;
 		}
 	}
-	long pe = BACK ? q + 8 : q - 1;
+	long pe = BACK ? q + N : q - 1;
 	if (pe >= 0 && pe < long(T))
 	{
 		edge = __ldg(node_of_pos + pe);
 		has_edge = true;
 	}
-	float4 lo[8], hi[8];
+	float4 lo[N], hi[N];
 #pragma unroll
-	for (int i = 0; i < 8; ++i)
+	for (int i = 0; i < N; ++i)
 		if (n[i] != NODE_DONE)
 		{
 			const float4* bp = reinterpret_cast<const float4*>(boxes + o[i]);
 			lo[i] = __ldg(bp), hi[i] = __ldg(bp + 1);
 		}
 #pragma unroll
-	for (int k = 0; k < 8; ++k)
+	for (int k = 0; k < N; ++k)
 	{
-		const int i = BACK ? 7 - k : k; // position inside the chunk of the k-th element in scan order
+		const int i = BACK ? N - 1 - k : k; // position inside the chunk of the k-th element in scan order
 		long p = q + i;
 		ScanElem x = scan_identity();
 		if (p >= 0 && p < long(T))
@@ -603,7 +709,7 @@ DEVFN void sa_load_chunk(const Box* __restrict__ boxes, const u32* __restrict__ 
 				// the element the sweep visited just before this one
 				const int ip = BACK ? i + 1 : i - 1;
 				bool head;
-				if (ip < 0 || ip > 7)
+				if (ip < 0 || ip > N - 1)
 					head = !has_edge || edge != n[i];
 				else
 					head = (BACK && p + 1 >= long(T)) || n[ip] != n[i];
@@ -626,8 +732,8 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 	const u32* __restrict__ order = sw.order[sweep >> 1];
 	float* out_area = sw.area + size_t(sweep) * (size_t(T) + 1);
 	const u32 base = tile * SA_TILE + threadIdx.x * SA_ITEMS;
-	const u32 Tpad = (T + 7u) & ~7u;
-	const long q = backward ? long(Tpad) - 8 - long(base) : long(base);
+	const u32 Tpad = (T + u32(SA_ITEMS) - 1) / SA_ITEMS * SA_ITEMS;
+	const long q = backward ? long(Tpad) - SA_ITEMS - long(base) : long(base);
 	ScanElem e[SA_ITEMS];
 	if (backward)
 		sa_load_chunk<true>(boxes, order, node_of_pos, T, q, e);
@@ -642,7 +748,7 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 	if (threadIdx.x < 32)
 	{
 		size_t region = size_t(sweep) * tiles;
-		ScanElem prefix = scan_chain_lookback<ScanElem, OpSegBox>(tile, total, chain_flags + region, chain_aggregate + region * SCAN_CHAIN_VALUE_BYTES, chain_inclusive + region * SCAN_CHAIN_VALUE_BYTES, epoch);
+		ScanElem prefix = sa_lookback(tile, total, chain_aggregate + region * SCAN_CHAIN_VALUE_BYTES, epoch);
 		if (threadIdx.x == 0)
 			s_prefix = prefix;
 	}
@@ -652,7 +758,7 @@ static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __r
 	for (int k = 0; k < SA_ITEMS; ++k)
 	{
 		prefix = scan_combine(prefix, e[k]);
-		long p = q + (backward ? 7 - k : k);
+		long p = q + (backward ? SA_ITEMS - 1 - k : k);
 		if (p >= 0 && p < long(T))
 		{
 			float sx = prefix.mx[0] - prefix.mn[0], sy = prefix.mx[1] - prefix.mn[1], sz = prefix.mx[2] - prefix.mn[2];
