@@ -500,10 +500,13 @@ DEVFN ScanElem scan_shfl_idx(const ScanElem& e, int src)
 }
 
 #ifndef CLODB_SA_THREADS
-#define CLODB_SA_THREADS 256
+#define CLODB_SA_THREADS 128
 #endif
 #ifndef CLODB_SA_ITEMS
 #define CLODB_SA_ITEMS 8
+#endif
+#ifndef CLODB_SA_MINBLOCKS
+#define CLODB_SA_MINBLOCKS 1
 #endif
 static const int SA_THREADS = CLODB_SA_THREADS;
 static const int SA_ITEMS = CLODB_SA_ITEMS;
@@ -722,7 +725,7 @@ DEVFN void sa_load_chunk(const Box* __restrict__ boxes, const u32* __restrict__ 
 
 // All six sweeps of a tree level (3 axis orders x forward/backward) in one launch: blockIdx.x = tile * 6 + sweep, so the six
 // independent tile chains advance concurrently and hide each other's look-back latency.
-static __global__ void __launch_bounds__(SA_THREADS) k_sa_chained(const Box* __restrict__ boxes, SweepArgs sw, const u32* __restrict__ node_of_pos,
+static __global__ void __launch_bounds__(SA_THREADS, CLODB_SA_MINBLOCKS) k_sa_chained(const Box* __restrict__ boxes, SweepArgs sw, const u32* __restrict__ node_of_pos,
     u32 T, u32 tiles, u32* chain_flags, char* chain_aggregate, char* chain_inclusive, u32 epoch)
 {
 	__shared__ ScanElem smem[SA_THREADS / 32];

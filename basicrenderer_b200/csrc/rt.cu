@@ -131,21 +131,57 @@ void dev_memset(void* p, int value, size_t bytes)
 	if (bytes)
 		CUDA_CHECK(cudaMemsetAsync(p, value, bytes, g_stream));
 }
+// Small control transfers (scalars, a few offsets) go through pinned memory: an upload is copied into a slot of a pinned
+// ring and enqueued without waiting (the ring is drained once per wrap-around, so a slot is never overwritten while its
+// copy is pending); a read-back lands in a pinned word and costs one stream synchronisation instead of a pageable-memory
+// staging copy. Larger transfers keep the plain path.
+static const size_t SMALL_XFER = 1024;
+static const size_t RING_SLOTS = 512;
+static char* g_pinned_ring = nullptr; // RING_SLOTS upload slots + one read-back slot
+static size_t g_ring_next = 0;
+
+static char* pinned_ring()
+{
+	if (!g_pinned_ring)
+		CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&g_pinned_ring), (RING_SLOTS + 1) * SMALL_XFER));
+	return g_pinned_ring;
+}
+
 void dev_h2d(void* dst, const void* src, size_t bytes)
 {
-	if (bytes)
+	if (!bytes)
+		return;
+	if (bytes <= SMALL_XFER)
 	{
-		CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
-		CUDA_CHECK(cudaStreamSynchronize(g_stream));
+		char* ring = pinned_ring();
+		if (g_ring_next == RING_SLOTS)
+		{
+			CUDA_CHECK(cudaStreamSynchronize(g_stream));
+			g_ring_next = 0;
+		}
+		char* slot = ring + g_ring_next++ * SMALL_XFER;
+		memcpy(slot, src, bytes);
+		CUDA_CHECK(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, g_stream));
+		return;
 	}
+	CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+	CUDA_CHECK(cudaStreamSynchronize(g_stream));
 }
 void dev_d2h(void* dst, const void* src, size_t bytes)
 {
-	if (bytes)
+	if (!bytes)
+		return;
+	if (bytes <= SMALL_XFER)
 	{
-		CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+		char* slot = pinned_ring() + RING_SLOTS * SMALL_XFER;
+		CUDA_CHECK(cudaMemcpyAsync(slot, src, bytes, cudaMemcpyDeviceToHost, g_stream));
 		CUDA_CHECK(cudaStreamSynchronize(g_stream));
+		memcpy(dst, slot, bytes);
+		g_ring_next = 0; // the stream is drained: every pending upload has landed
+		return;
 	}
+	CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+	CUDA_CHECK(cudaStreamSynchronize(g_stream));
 }
 void dev_d2d(void* dst, const void* src, size_t bytes)
 {
