@@ -452,5 +452,5 @@ _product = None
 def load(device: int = 0) -> ClodLib:
     global _product
     if _product is None:
-        _product = ClodLib(PRODUCT_LIB, device)
+        _product = ClodLib(os.environ.get("CLODB200_LIB", PRODUCT_LIB), device)  # CLODB200_LIB: tuning variants (tools/)
     return _product

@@ -726,7 +726,7 @@ DEVFN void sa_load_chunk(const Box* __restrict__ boxes, const u32* __restrict__ 
 // All six sweeps of a tree level (3 axis orders x forward/backward) in one launch: blockIdx.x = tile * 6 + sweep, so the six
 // independent tile chains advance concurrently and hide each other's look-back latency.
 static __global__ void __launch_bounds__(SA_THREADS, CLODB_SA_MINBLOCKS) k_sa_chained(const Box* __restrict__ boxes, SweepArgs sw, const u32* __restrict__ node_of_pos,
-    u32 T, u32 tiles, u32* chain_flags, char* chain_aggregate, char* chain_inclusive, u32 epoch)
+    u32 T, u32 tiles, char* chain_desc, u32 epoch)
 {
 	__shared__ ScanElem smem[SA_THREADS / 32];
 	__shared__ ScanElem s_prefix;
@@ -751,7 +751,7 @@ static __global__ void __launch_bounds__(SA_THREADS, CLODB_SA_MINBLOCKS) k_sa_ch
 	if (threadIdx.x < 32)
 	{
 		size_t region = size_t(sweep) * tiles;
-		ScanElem prefix = sa_lookback(tile, total, chain_aggregate + region * SCAN_CHAIN_VALUE_BYTES, epoch);
+		ScanElem prefix = sa_lookback(tile, total, chain_desc + region * SCAN_CHAIN_VALUE_BYTES, epoch);
 		if (threadIdx.x == 0)
 			s_prefix = prefix;
 	}
@@ -780,11 +780,37 @@ static void seg_area_scan_all(const Box* boxes, u32* const* order, const u32* no
 	for (int k = 0; k < 3; ++k)
 		sw.order[k] = order[k];
 	sw.area = areas;
-	LAUNCH_GRID(k_sa_chained, size_t(tiles) * 6, SA_THREADS, boxes, sw, node_of_pos, T, tiles, g_scan_chain.flags, g_scan_chain.aggregate, g_scan_chain.inclusive, epoch);
+	LAUNCH_GRID(k_sa_chained, size_t(tiles) * 6, SA_THREADS, boxes, sw, node_of_pos, T, tiles, g_scan_chain.box_desc, epoch);
 }
 #endif
 
 // (cost, axis, index) argmin per large node (bvhPivot over count > max_triangles, vertices == NULL)
+DEVFN u64 pivot_key_at(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const float* __restrict__ larea, const float* __restrict__ rarea, int axis, size_t p,
+    const SplitParams& sp, u32* node_out)
+{
+	const u64 none = ~u64(0);
+	u32 n = node_of_pos[p];
+	if (n == NODE_DONE)
+		return none;
+	u32 count = node_count[n];
+	if (count <= sp.max_triangles)
+		return none;
+	u32 i = u32(p) - node_begin[n];
+	u32 mn = sp.min_triangles;
+	bool aligned = count >= mn * 2 && bvh_divisible(count, mn, sp.max_triangles);
+	u32 end = aligned ? count - mn : count - 1;
+	if (i < mn - 1 || i >= end)
+		return none;
+	float cost;
+	if (!pivot_cost(i, count, mn, sp.max_triangles, aligned, larea[p], rarea[p + 1], 0, false, sp.fill_weight, sp.max_triangles, &cost))
+		return none;
+	if (!(cost < FLT_MAX) || cost < 0.f)
+		return none;
+	*node_out = n;
+	return (u64(__float_as_uint(cost)) << 32) | (u64(axis) << 30) | u64(i);
+}
+
+#ifdef CLODB_EMU
 KERNEL k_pivot_large(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const float* __restrict__ areas, u64* node_best, u32 T, SplitParams sp)
 {
 	size_t gi = GTID;
@@ -792,47 +818,91 @@ KERNEL k_pivot_large(const u32* __restrict__ node_of_pos, const u32* __restrict_
 		return;
 	int axis = int(gi / T);
 	size_t p = gi - size_t(axis) * T;
-	const float* larea = areas + size_t(axis * 2) * (size_t(T) + 1);
-	const float* rarea = areas + size_t(axis * 2 + 1) * (size_t(T) + 1);
-	u32 n = node_of_pos[p];
-	if (n == NODE_DONE)
-		return;
-	u32 count = node_count[n];
-	if (count <= sp.max_triangles)
-		return;
-	u32 i = u32(p) - node_begin[n];
-	u32 mn = sp.min_triangles;
-	bool aligned = count >= mn * 2 && bvh_divisible(count, mn, sp.max_triangles);
-	u32 end = aligned ? count - mn : count - 1;
-	if (i < mn - 1 || i >= end)
-		return;
-	float cost;
-	if (!pivot_cost(i, count, mn, sp.max_triangles, aligned, larea[p], rarea[p + 1], 0, false, sp.fill_weight, sp.max_triangles, &cost))
-		return;
-	if (!(cost < FLT_MAX) || cost < 0.f)
-		return;
-	u64 key = (u64(__float_as_uint(cost)) << 32) | (u64(axis) << 30) | u64(i);
-#ifndef CLODB_EMU
-	// warp-aggregate: lanes of one warp mostly sit in the same node
-	unsigned active = __activemask();
-	unsigned peers = __match_any_sync(active, n);
-	u64 best = key;
-	for (int d = 16; d >= 1; d >>= 1)
-	{
-		u64 other = __shfl_xor_sync(active, best, d);
-		unsigned src = (threadIdx.x & 31) ^ d;
-		if (((peers >> src) & 1u) && other < best)
-			best = other;
-	}
-	// after a full xor butterfly restricted to peers the minimum may not have reached every peer; let every lane whose
-	// key equals its own reduction result publish (cheap: same address, at most a few per warp)
-	if (best == key)
-		atomicMin(reinterpret_cast<unsigned long long*>(&node_best[n]), (unsigned long long)key);
-#else
-	if (key < node_best[n])
+	u32 n = 0;
+	u64 key = pivot_key_at(node_of_pos, node_begin, node_count, areas + size_t(axis * 2) * (size_t(T) + 1), areas + size_t(axis * 2 + 1) * (size_t(T) + 1), axis, p, sp, &n);
+	if (key != ~u64(0) && key < node_best[n])
 		node_best[n] = key;
-#endif
 }
+#else
+// Four consecutive positions per thread. Large nodes are long runs of positions, so nearly every warp sits inside one node:
+// its 128 keys are reduced with two redux operations and cost one atomicMin. Warps that straddle nodes fall back to a
+// match_any reduction per element.
+static const int PV_ITEMS = 4;
+static __global__ void __launch_bounds__(256) k_pivot_large(const u32* __restrict__ node_of_pos, const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const float* __restrict__ areas, u64* node_best, u32 T,
+    SplitParams sp)
+{
+	const u64 none = ~u64(0);
+	const size_t tid = GTID;
+	const size_t Tq = (size_t(T) + PV_ITEMS - 1) / PV_ITEMS;
+	const u32 lane = threadIdx.x & 31;
+	u64 key[PV_ITEMS];
+	u32 node[PV_ITEMS];
+	u64 best = none;
+	u32 nref = NODE_DONE;
+	bool same = true;
+	if (tid < Tq * 3)
+	{
+		int axis = int(tid / Tq);
+		size_t p0 = (tid - size_t(axis) * Tq) * PV_ITEMS;
+		const float* larea = areas + size_t(axis * 2) * (size_t(T) + 1);
+		const float* rarea = areas + size_t(axis * 2 + 1) * (size_t(T) + 1);
+#pragma unroll
+		for (int j = 0; j < PV_ITEMS; ++j)
+		{
+			key[j] = none;
+			node[j] = NODE_DONE;
+			if (p0 + j < T)
+				key[j] = pivot_key_at(node_of_pos, node_begin, node_count, larea, rarea, axis, p0 + j, sp, &node[j]);
+			if (key[j] != none)
+			{
+				if (nref == NODE_DONE)
+					nref = node[j];
+				same = same && node[j] == nref;
+				best = key[j] < best ? key[j] : best;
+			}
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int j = 0; j < PV_ITEMS; ++j)
+			key[j] = none, node[j] = NODE_DONE;
+	}
+	unsigned have = __ballot_sync(0xffffffffu, nref != NODE_DONE);
+	if (!have)
+		return;
+	u32 warp_ref = __shfl_sync(0xffffffffu, nref, __ffs(have) - 1);
+	if (__all_sync(0xffffffffu, nref == NODE_DONE || (same && nref == warp_ref)))
+	{
+		u32 hi = u32(best >> 32), lo = u32(best);
+		u32 mhi = __reduce_min_sync(0xffffffffu, hi);
+		u32 mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+		if (lane == 0)
+			atomicMin(reinterpret_cast<unsigned long long*>(&node_best[warp_ref]), (unsigned long long)((u64(mhi) << 32) | mlo));
+		return;
+	}
+#pragma unroll
+	for (int j = 0; j < PV_ITEMS; ++j)
+	{
+		unsigned active = __ballot_sync(0xffffffffu, key[j] != none);
+		if (key[j] == none)
+			continue;
+		unsigned peers = __match_any_sync(active, node[j]);
+		u64 m = key[j];
+		for (int d = 16; d >= 1; d >>= 1)
+		{
+			u64 other = __shfl_xor_sync(active, m, d);
+			unsigned src = lane ^ d;
+			if (((peers >> src) & 1u) && other < m)
+				m = other;
+		}
+		// after a butterfly restricted to peers the minimum may not have reached every peer; every lane whose key equals its
+		// own reduction result publishes (same address, at most a few per warp)
+		if (m == key[j])
+			atomicMin(reinterpret_cast<unsigned long long*>(&node_best[node[j]]), (unsigned long long)key[j]);
+	}
+}
+#endif
 
 KERNEL k_reset_best(u64* node_best, u32 n_nodes)
 {
@@ -1419,7 +1489,11 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 		if (any_large)
 		{
 			seg_area_scan_all(boxes, order, node_of_pos, node_begin, node_count, areas, T, temp);
+#ifdef CLODB_EMU
 			LAUNCH(k_pivot_large, size_t(T) * 3, node_of_pos, node_begin, node_count, areas, node_best, T, sp);
+#else
+			LAUNCH(k_pivot_large, ((size_t(T) + PV_ITEMS - 1) / PV_ITEMS) * 3, node_of_pos, node_begin, node_count, areas, node_best, T, sp);
+#endif
 			LAUNCH(k_resolve_nodes, n_nodes, node_begin, node_count, node_best, node_split, n_nodes, depth, order[0], order[1], order[2], boxes, tri, boundary, sp, 1, nullptr);
 		}
 #ifdef CLODB_EMU

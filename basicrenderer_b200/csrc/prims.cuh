@@ -181,10 +181,12 @@ DEVFN T block_exclusive_scan(T v, T* block_total, T* smem)
 // finished). The combine is applied in predecessor order, so non-commutative (segmented) operators are supported.
 struct ScanChain
 {
-	u32* flags = nullptr;    // per tile: (epoch << 2) | {1 = aggregate ready, 2 = inclusive prefix ready}
-	char* aggregate = nullptr; // SCAN_CHAIN_VALUE_BYTES per tile
-	char* inclusive = nullptr;
-	char* desc = nullptr; // packed {status, value} descriptors of the 4-/8-byte scans, 16 bytes per tile
+	// Packed {status, value} tile descriptors, one array per descriptor format. The formats must not share memory: a
+	// stale 16-byte descriptor of an 8-byte scan read as the 8-byte descriptor of a 4-byte scan puts the high half of
+	// an old *value* where the tag is expected, and values such as (group + 1) << 32 | bits do collide with small epochs.
+	char* desc = nullptr;     // 4-byte scans: 8-byte {tag, value} words at a 16-byte stride
+	char* desc64 = nullptr;   // 8-byte scans: 16-byte {value, tag} words
+	char* box_desc = nullptr; // segmented box scans (clusterize.cu): two 16-byte {tag, xyz} words per tile
 	size_t capacity_tiles = 0;
 	u32 epoch = 0;
 };
@@ -248,84 +250,6 @@ DEVFN T shfl_idx_struct(const T& v, int lane)
 	for (int k = 0; k < int(sizeof(T) / 4); ++k)
 		dst[k] = __shfl_sync(0xffffffffu, src[k], lane);
 	return r;
-}
-
-// Called by all 32 lanes of warp 0 with the tile's aggregate; returns the tile's exclusive prefix (valid in every lane)
-// and publishes the tile's inclusive prefix. Combine(a, b): a precedes b.
-template <typename T, typename Op>
-DEVFN T scan_chain_lookback(u32 tile, const T& tile_aggregate, u32* flags, char* aggregate, char* inclusive, u32 epoch)
-{
-	int lane = threadIdx.x & 31;
-	u32 tag_agg = (epoch << 2) | 1u, tag_inc = (epoch << 2) | 2u;
-	if (tile == 0)
-	{
-		if (lane == 0)
-		{
-			st_value<T>(inclusive, 0, tile_aggregate);
-			__threadfence();
-			*reinterpret_cast<volatile u32*>(flags) = tag_inc;
-		}
-		return Op::identity();
-	}
-	// Segmented operators: when the tile contains a segment head, everything after the tile only depends on the tile itself,
-	// so its aggregate already is its inclusive prefix and can be published as such before looking back (successors then
-	// stop their look-back here instead of walking further).
-	const bool independent = Op::prefix_independent(tile_aggregate);
-	if (lane == 0)
-	{
-		if (independent)
-		{
-			st_value<T>(inclusive, tile, tile_aggregate);
-			__threadfence();
-			*reinterpret_cast<volatile u32*>(flags + tile) = tag_inc;
-		}
-		else
-		{
-			st_value<T>(aggregate, tile, tile_aggregate);
-			__threadfence();
-			*reinterpret_cast<volatile u32*>(flags + tile) = tag_agg;
-		}
-	}
-	T prefix = Op::identity(); // combination of the predecessors visited so far (nearest block of them)
-	int p = int(tile) - 1;
-	for (;;)
-	{
-		int idx = p - lane;
-		u32 f;
-		for (;;)
-		{
-			f = idx >= 0 ? ld_volatile_u32(flags + idx) : tag_inc;
-			bool ready = f == tag_agg || f == tag_inc;
-			if (__all_sync(0xffffffffu, ready))
-				break;
-		}
-		__threadfence();
-		unsigned inc_mask = __ballot_sync(0xffffffffu, f == tag_inc);
-		int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32; // nearest predecessor whose inclusive prefix is known
-		T v = Op::identity();
-		if (idx >= 0 && lane <= first_inc)
-			v = f == tag_inc ? ld_cg_value<T>(inclusive, size_t(idx)) : ld_cg_value<T>(aggregate, size_t(idx));
-		// ordered reduction: lane L is farther back than lane L-1, so it is the left operand
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			T t = shfl_down_struct(v, d);
-			if (lane + d < 32)
-				v = Op::apply(t, v);
-		}
-		v = shfl_idx_struct(v, 0);
-		prefix = Op::apply(v, prefix);
-		if (inc_mask)
-			break;
-		p -= 32;
-	}
-	if (lane == 0 && !independent)
-	{
-		st_value<T>(inclusive, tile, Op::apply(prefix, tile_aggregate));
-		__threadfence();
-		*reinterpret_cast<volatile u32*>(flags + tile) = tag_inc;
-	}
-	return prefix;
 }
 
 // ---- packed descriptors for 4- and 8-byte values ---------------------------------------------------------------------
@@ -565,13 +489,13 @@ static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena
 		const size_t tile = size_t(SCAN_LARGE_THREADS) * SCAN_LARGE_ITEMS;
 		size_t nblocks = (n + tile - 1) / tile;
 		scan_chain_reserve(nblocks);
-		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>), nblocks, SCAN_LARGE_THREADS, in, out, n, g_scan_chain.desc, epoch, total);
+		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>), nblocks, SCAN_LARGE_THREADS, in, out, n, sizeof(T) == 8 ? g_scan_chain.desc64 : g_scan_chain.desc, epoch, total);
 	}
 	else
 	{
 		size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
 		scan_chain_reserve(nblocks);
-		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>), nblocks, SCAN_THREADS, in, out, n, g_scan_chain.desc, epoch, total);
+		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>), nblocks, SCAN_THREADS, in, out, n, sizeof(T) == 8 ? g_scan_chain.desc64 : g_scan_chain.desc, epoch, total);
 	}
 }
 

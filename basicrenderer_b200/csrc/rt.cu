@@ -295,16 +295,15 @@ void scan_chain_reserve(size_t tiles)
 		return;
 	size_t cap = std::max<size_t>(tiles * 2, size_t(1) << 16);
 	CUDA_CHECK(cudaStreamSynchronize(g_stream));
-	dev_free(g_scan_chain.flags);
-	dev_free(g_scan_chain.aggregate);
-	dev_free(g_scan_chain.inclusive);
 	dev_free(g_scan_chain.desc);
-	g_scan_chain.flags = static_cast<u32*>(dev_malloc(cap * sizeof(u32)));
-	g_scan_chain.aggregate = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
-	g_scan_chain.inclusive = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
+	dev_free(g_scan_chain.desc64);
+	dev_free(g_scan_chain.box_desc);
 	g_scan_chain.desc = static_cast<char*>(dev_malloc(cap * 16));
-	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.flags, 0, cap * sizeof(u32), g_stream));
+	g_scan_chain.desc64 = static_cast<char*>(dev_malloc(cap * 16));
+	g_scan_chain.box_desc = static_cast<char*>(dev_malloc(cap * SCAN_CHAIN_VALUE_BYTES));
 	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.desc, 0, cap * 16, g_stream));
+	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.desc64, 0, cap * 16, g_stream));
+	CUDA_CHECK(cudaMemsetAsync(g_scan_chain.box_desc, 0, cap * SCAN_CHAIN_VALUE_BYTES, g_stream));
 	g_scan_chain.capacity_tiles = cap;
 }
 #endif
@@ -318,8 +317,27 @@ void Arena::init(size_t bytes)
 	high_water = 0;
 }
 
+void* Arena::debug_alloc(size_t at, size_t bytes)
+{
+	void* p = dev_malloc(bytes);
+	debug_blocks.push_back(std::make_pair(at, p));
+	return p;
+}
+
+void Arena::debug_release(size_t m)
+{
+	dev_sync();
+	while (!debug_blocks.empty() && debug_blocks.back().first >= m)
+	{
+		dev_free(debug_blocks.back().second);
+		debug_blocks.pop_back();
+	}
+}
+
 void Arena::destroy()
 {
+	if (!debug_blocks.empty())
+		debug_release(0);
 	if (base)
 		dev_free(base);
 	base = nullptr;

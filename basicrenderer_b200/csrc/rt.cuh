@@ -13,6 +13,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #ifdef CLODB_EMU
@@ -258,12 +259,26 @@ struct Arena
 	}
 	void release(size_t m)
 	{
+		if (!debug_blocks.empty())
+			debug_release(m);
 		offset = m;
 	}
+
+	// CLODB200_DEBUG_MALLOC: every arena allocation becomes its own device allocation (freed when its scope is released), so
+	// that compute-sanitizer sees overruns between neighbouring arrays of the slab. Development aid; off by default.
+	std::vector<std::pair<size_t, void*>> debug_blocks;
+	void* debug_alloc(size_t at, size_t bytes);
+	void debug_release(size_t m);
 
 	void* alloc_bytes(size_t bytes)
 	{
 		size_t aligned = (offset + 255) & ~size_t(255);
+		static const bool debug_malloc = getenv("CLODB200_DEBUG_MALLOC") != nullptr;
+		if (debug_malloc && aligned + bytes <= capacity)
+		{
+			offset = aligned + bytes;
+			return debug_alloc(aligned, bytes);
+		}
 		if (aligned + bytes > capacity)
 			throw Error("clodb200: device arena exhausted (need " + std::to_string(aligned + bytes) + " of " + std::to_string(capacity) + " bytes)");
 		offset = aligned + bytes;
