@@ -198,6 +198,9 @@ void dev_sync()
 void profile_mark(const char*, int, size_t)
 {
 }
+void profile_set_last_work(size_t)
+{
+}
 std::string profile_report()
 {
 	return std::string();
@@ -244,6 +247,12 @@ void profile_mark(const char* kernel_name, int end, size_t threads)
 	{
 		CUDA_CHECK(cudaEventRecord(g_spans.back().stop, g_stream));
 	}
+}
+
+void profile_set_last_work(size_t items)
+{
+	if (!g_spans.empty())
+		g_spans.back().threads = items;
 }
 
 std::string profile_report()

@@ -217,6 +217,8 @@ extern int g_sync_debug;
 // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg); off by default
 extern int g_profile;
 void profile_mark(const char* kernel_name, int end, size_t threads);
+// persistent kernels: replace the thread count of the span just recorded by the number of work items it processed
+void profile_set_last_work(size_t items);
 // drains recorded events; returns "name,launches,total_ms,total_threads\n" lines sorted by time
 std::string profile_report();
 

@@ -1178,7 +1178,7 @@ DEVFN bool wave_decide_coop8(u32 k, bool valid, unsigned gmask, u32 lane8, const
 // rounds are separated by grid-wide barriers instead of kernel launches.
 //   list[0] / state[0] hold the initial work list and its length; state[1] must be zero on entry;
 //   state[0..1] list counters, state[2] running round tag, state[3] rounds executed, state[4] undecided left,
-//   state[5] total rounds of all passes, state[6] max rounds in a pass
+//   state[5] total rounds of all passes, state[6] max rounds in a pass, state[8..9] (u64) work items (candidate x round) of this launch
 struct WaveArgs
 {
 	const u32* sorted_cand;
@@ -1208,10 +1208,12 @@ static __global__ void __launch_bounds__(WAVE_THREADS, 1) k_wave_rounds(WaveArgs
 	u32 tag = a.state[2];
 	const u32* cur = a.list[0];
 	u32 round = 0;
+	unsigned long long items = 0;
 	while (n != 0)
 	{
 		++round;
 		++tag;
+		items += n;
 		for (u32 i = gtid; i < n; i += gsize)
 			wave_publish_item(cur[i], a.sorted_cand, a.cand_v0, a.cand_v1, a.remap, a.vmin_any, a.vmin_src, tag);
 		grid.sync();
@@ -1261,6 +1263,7 @@ static __global__ void __launch_bounds__(WAVE_THREADS, 1) k_wave_rounds(WaveArgs
 		a.state[4] = n;
 		a.state[5] += round;
 		a.state[6] = a.state[6] > round ? a.state[6] : round;
+		*reinterpret_cast<unsigned long long*>(a.state + 8) = items;
 	}
 }
 #endif
@@ -2394,8 +2397,8 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 
 	dev_memset(vmin_any, 0xff, size_t(vertex_count) * 8);
 	dev_memset(vmin_src, 0xff, size_t(vertex_count) * 8);
-	u32* wave_state = temp.alloc<u32>(8);
-	dev_memset(wave_state, 0, 8 * sizeof(u32));
+	u32* wave_state = temp.alloc<u32>(12);
+	dev_memset(wave_state, 0, 12 * sizeof(u32));
 #ifndef CLODB_EMU
 	static u32 wave_max_blocks = 0;
 	if (!wave_max_blocks)
@@ -2476,6 +2479,11 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 				static const u32 blocks_per_sm_cap = getenv("CLODB200_WAVE_BLOCKS") ? u32(atoi(getenv("CLODB200_WAVE_BLOCKS"))) : 0u;
 				u32 blocks = std::min<u32>(blocks_per_sm_cap ? std::min(wave_max_blocks, blocks_per_sm_cap) : wave_max_blocks, (cand_total + WAVE_THREADS / 8 - 1) / (WAVE_THREADS / 8));
 				LAUNCH_COOP(k_wave_rounds, blocks, WAVE_THREADS, wa);
+				if (g_profile)
+				{
+					std::vector<u32> ws_now = dev_download(wave_state, 12);
+					profile_set_last_work((size_t(ws_now[9]) << 32) | ws_now[8]);
+				}
 				if (log_rounds)
 				{
 					std::vector<u32> lg = dev_download(wa.round_log, 512);

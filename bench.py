@@ -38,18 +38,22 @@ PROTECT_MASK = 7
 # Algorithmic bytes per thread of the kernels that can dominate a step (DESIGN.md "Kernels" table derives each figure):
 # what the kernel must read and write once if every operand moved exactly once.
 KERNEL_BYTES_PER_THREAD = {
-    # segmented SAH area scan, 4 elements per thread: order u32 + gathered box 32 B + node id u32 (+ area f32 out)
-    "k_sa_chained": 4 * (4 + 32 + 4 + 4),
+    # segmented SAH area scan, 8 elements per thread (SA_ITEMS): order u32 + gathered box 32 B + node id u32 + area f32 out
+    "k_sa_chained": 8 * (4 + 32 + 4 + 4),
     # radix sort scatter, 8 keys per thread: key in + key out + value in + value out (u32 keys)
     "(k_rs_scatter<K>)": 8 * 16,
     "k_rs_scatter<K>": 8 * 16,
     "(k_rs_hist<K>)": 8 * 4,
     "k_rs_hist<K>": 8 * 4,
-    "k_pivot_large": 4 + 4 + 4 + 8,
+    # pivot search, 4 positions per thread: node id + prefix area + suffix area (node tables stay in cache)
+    "k_pivot_large": 4 * (4 + 4 + 4),
     "k_partition": 4 + 4 + 4 + 1 + 4 + 4,
     "k_side_flags": 4 + 1 + 4,
     "k_mark_sides": 4 + 4 + 1 + 8,
     "k_update_node_of_pos": 4 + 4 + 4,
+    # persistent wavefront kernel: the profile reports (candidate x round) work items instead of threads; per item one publish
+    # and one decide step: sorted id 4 + (v0, v1) 8 + remap 8 + three 8-byte vertex minima
+    "k_wave_rounds": 4 + 8 + 8 + 3 * 8,
     "k_wave_decide": 1 + 4 + 8 + 8 + 16,
     "k_wave_publish": 1 + 4 + 8 + 3 * 8,
     "k_rank": 9 + 2 * (44 + 12) + 4 + 8,
@@ -57,6 +61,10 @@ KERNEL_BYTES_PER_THREAD = {
     "k_cluster_bounds": 128 * 3 * 16 + 16,
     # chained single-pass scan, 8 u32 elements per thread, read once + written once
     "(k_scan_chained<T, Op>)": 8 * 8,
+    "(k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>)": 8 * 8,
+    "(k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>)": 16 * 8,
+    # persistent kernels: no per-thread figure (work is data dependent); reported without a roofline fraction
+
 }
 
 
