@@ -162,6 +162,9 @@ class ClodLib:
         self._check(self._lib.clodb200_primExclusiveScanU32(_ptr(values), _ptr(out), values.size, _ptr(total), repeat, C.byref(ms)))
         return out, int(total[0]), ms.value
 
+    def prim_set_scan_epoch(self, epoch: int):
+        self._check(self._lib.clodb200_primSetScanEpoch(C.c_uint(epoch)))
+
     def prim_exclusive_max_scan_u64(self, values: np.ndarray, repeat: int = 1):
         values = np.ascontiguousarray(values, dtype=np.uint64)
         out = np.empty_like(values)

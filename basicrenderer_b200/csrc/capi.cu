@@ -1356,6 +1356,18 @@ int clodb200_primExclusiveMaxScanU64(const uint64_t* in, uint64_t* out, size_t n
 	});
 }
 
+int clodb200_primSetScanEpoch(unsigned int epoch)
+{
+	return guarded([&]() -> int {
+#ifndef CLODB_EMU
+		g_scan_chain.epoch = epoch & 0x3fffffffu;
+#else
+		(void)epoch;
+#endif
+		return CLODB200_OK;
+	});
+}
+
 int clodb200_primSortPairsU32(unsigned int* keys, unsigned int* values, size_t n, int bit_lo, int bit_hi, int repeat, float* ms)
 {
 	return guarded([&]() -> int {

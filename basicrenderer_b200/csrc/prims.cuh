@@ -484,19 +484,20 @@ static inline void exclusive_scan(const T* in, T* out, size_t n, T* total, Arena
 		return;
 	}
 	u32 epoch = scan_chain_next_epoch();
-	if (n >= SCAN_LARGE_N)
-	{
-		const size_t tile = size_t(SCAN_LARGE_THREADS) * SCAN_LARGE_ITEMS;
-		size_t nblocks = (n + tile - 1) / tile;
-		scan_chain_reserve(nblocks);
-		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>), nblocks, SCAN_LARGE_THREADS, in, out, n, sizeof(T) == 8 ? g_scan_chain.desc64 : g_scan_chain.desc, epoch, total);
-	}
+	const bool large = n >= SCAN_LARGE_N;
+	const size_t tile = large ? size_t(SCAN_LARGE_THREADS) * SCAN_LARGE_ITEMS : size_t(SCAN_TILE);
+	size_t nblocks = (n + tile - 1) / tile;
+	scan_chain_reserve(nblocks); // may reallocate the descriptor arrays: take the pointer afterwards
+#ifdef CLODB_DEBUG_SHARED_DESC
+	// build variant for tests/test_prims.py::test_scan_descriptor_formats_do_not_alias: the pre-fix layout, to show the test bites
+	char* const chain_desc = g_scan_chain.desc;
+#else
+	char* const chain_desc = sizeof(T) == 8 ? g_scan_chain.desc64 : g_scan_chain.desc;
+#endif
+	if (large)
+		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>), nblocks, SCAN_LARGE_THREADS, in, out, n, chain_desc, epoch, total);
 	else
-	{
-		size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-		scan_chain_reserve(nblocks);
-		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>), nblocks, SCAN_THREADS, in, out, n, sizeof(T) == 8 ? g_scan_chain.desc64 : g_scan_chain.desc, epoch, total);
-	}
+		LAUNCH_GRID((k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>), nblocks, SCAN_THREADS, in, out, n, chain_desc, epoch, total);
 }
 
 // ---- radix sort ------------------------------------------------------------------------------------------------

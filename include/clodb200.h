@@ -295,6 +295,9 @@ size_t clodb200_profileReport(char* buffer, size_t capacity);
 int clodb200_primExclusiveScanU32(const unsigned int* in, unsigned int* out, size_t n, unsigned int* total, int repeat, float* ms);
 int clodb200_primExclusiveMaxScanU64(const uint64_t* in, uint64_t* out, size_t n, int repeat, float* ms);
 int clodb200_primSortPairsU32(unsigned int* keys, unsigned int* values, size_t n, int bit_lo, int bit_hi, int repeat, float* ms);
+/* Test hook: sets the call epoch of the chained scans (every scan call takes the next epoch and tags its tile descriptors
+ * with it). Lets a test put the epoch where stale descriptors of another scan format would alias it (tests/test_prims.py). */
+int clodb200_primSetScanEpoch(unsigned int epoch);
 /* The corner-angle arccosine of the tangent generator: the reference's `acos(float)` (Utilities/mikktspace.cpp:1421)
  * resolves to the C library's acosf; out[i] must equal it bit for bit on [-1, 1] (NaN outside). */
 int clodb200_primAcosf(const float* in, float* out, size_t n);

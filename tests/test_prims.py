@@ -39,3 +39,28 @@ def test_sort_pairs_u32_is_stable(lib, n, bits):
     order = np.argsort(keys, kind="stable")
     assert np.array_equal(v, vals[order])
     assert np.array_equal(k, keys[order])
+
+
+_alias_round = [0]
+
+
+def test_scan_descriptor_formats_do_not_alias(lib):
+    """Regression: the 8-byte max-scan leaves 16-byte {value, tag} tile descriptors; a 4-byte scan reading 8-byte
+    {tag, value} words from the same memory would see the high half of a stale value as its tag. The simplifier's tagged
+    errors are (group + 1) << 32 | bits, which equals (epoch << 2) | status for small epochs: the first build of a process on
+    a mesh with many groups took garbage look-back prefixes. Here every stale inclusive prefix carries
+    exactly the inclusive tag of the next call's epoch, and a 4-byte scan is that next call. The epoch only ever
+    jumps forward (descriptors of the same format rely on epochs never repeating)."""
+    n = 2048 * 900
+    rng = np.random.default_rng(5)
+    v = rng.integers(0, 3, n, dtype=np.uint32)
+    ref = np.concatenate([[0], np.cumsum(v, dtype=np.uint64)]).astype(np.uint32)
+    for _ in range(40):
+        _alias_round[0] += 1
+        base = 50_000_000 + 10 * _alias_round[0]
+        lib.prim_set_scan_epoch(base)
+        # the max-scan takes epoch base + 1; its stale descriptors carry the inclusive tag of the scan that follows it
+        stale = np.full(n, ((4 * (base + 2) + 2) << 32) | 0x3F800000, dtype=np.uint64)  # tag_inc(base + 2) : bits of 1.0f
+        lib.prim_exclusive_max_scan_u64(stale)
+        out, total, _ = lib.prim_exclusive_scan_u32(v)  # epoch base + 2
+        assert np.array_equal(out, ref[:-1]) and total == int(ref[-1])
