@@ -991,7 +991,10 @@ struct OpSegCount
 	}
 };
 
-static const int PT_THREADS = 256;
+#ifndef CLODB_PT_THREADS
+#define CLODB_PT_THREADS 256
+#endif
+static const int PT_THREADS = CLODB_PT_THREADS;
 static const int PT_ITEMS = 8;
 static const int PT_TILE = PT_THREADS * PT_ITEMS;
 

@@ -48,6 +48,8 @@ KERNEL_BYTES_PER_THREAD = {
     # pivot search, 4 positions per thread: node id + prefix area + suffix area (node tables stay in cache)
     "k_pivot_large": 4 * (4 + 4 + 4),
     "k_partition": 4 + 4 + 4 + 1 + 4 + 4,
+    # fused side flags + segmented count + stable partition, 8 positions per thread: order + node id + side byte in, order out
+    "k_partition_chained": 8 * (4 + 4 + 1 + 4),
     "k_side_flags": 4 + 1 + 4,
     "k_mark_sides": 4 + 4 + 1 + 8,
     "k_update_node_of_pos": 4 + 4 + 4,
@@ -146,10 +148,101 @@ def _pin(a: np.ndarray) -> np.ndarray:
 _PINNED = []
 
 
+def run_scene_batch(args):
+    """CLODB200_BENCH_WORKLOAD=C4 (opt-in): a scene batch of independent meshes of the C4 generator (type = i mod 3, log-uniform
+    triangle budgets), sharded by mesh across the ranks (LPT, basicrenderer_b200/sharding.py); every rank builds its meshes one
+    after the other and the cache metadata blobs are gathered to all ranks. Total work is fixed as N grows (strong scaling).
+    CLODB200_BENCH_MESHES / CLODB200_BENCH_BATCH_TRIS bound the batch (default 48 meshes, 48 M triangles: the C4 mix at 1/20 scale)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = _dist()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    from basicrenderer_b200 import artifacts as art
+    from basicrenderer_b200 import load, sharding
+
+    lib = load(local)
+    count = int(os.environ.get("CLODB200_BENCH_MESHES", 48))
+    total = float(os.environ.get("CLODB200_BENCH_BATCH_TRIS", 48e6))
+    budgets = meshgen.scene_batch_sizes(count, total)
+    mine = sharding.assign_meshes([int(b) for b in budgets], world)[rank]
+    meshes = [meshgen.scene_mesh(i, budgets[i]) for i in mine]
+    host = [(_pin(art.interleave(m.positions, m.normals)), _pin(m.indices)) for m in meshes]
+    handles = [lib.upload_geometry(v, i, art.VERTEX_NORMALS) for v, i in host]
+    my_tris = sum(m.triangle_count for m in meshes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(resident):
+        blobs = []
+        for k, mesh_id in enumerate(mine):
+            rec = lib.build_artifacts_resident(handles[k], views=True, keep_handle=True) if resident else lib.build_artifacts(host[k][0], host[k][1], art.VERTEX_NORMALS, views=True, keep_handle=True)
+            blobs.append(lib.serialize_metadata(rec, f"clod_mesh{mesh_id}.clodbin", "bench", f"/mesh{mesh_id}"))
+            lib.free_artifacts(rec)
+        gathered = sharding.gather_metadata(list(mine), blobs)
+        assert len(gathered) == count
+        return sum(len(b) for b in gathered.values())
+
+    for _ in range(args.warmup):
+        step(True)
+    stop = threading.Event()
+    clock_samples = []
+    sampler = threading.Thread(target=_sample_clocks, args=(stop, clock_samples), daemon=True)
+    sampler.start()
+    barrier()
+    launches0 = lib.launch_count
+    lib.timer_start()
+    for _ in range(args.steps):
+        blob_bytes = step(True)
+    ms = lib.timer_stop_ms()
+    launches = lib.launch_count - launches0
+    barrier()
+    stop.set()
+    sampler.join()
+    step(False)
+    barrier()
+    lib.timer_start()
+    for _ in range(args.steps):
+        step(False)
+    ms_e2e = lib.timer_stop_ms()
+    barrier()
+    tris = float(my_tris)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        tt = torch.tensor([tris], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        tris = float(tt[0])
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        print(json.dumps({
+            "metric": "Mtris/s full cluster-LOD DAG build", "value": tris / (ms_per_step * 1e-3) / 1e6, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": f"C4 shape: scene batch of {count} independent meshes ({int(tris)} triangles; sphere / heightfield / torus, log-uniform budgets {int(budgets.min())}..{int(budgets.max())}), "
+                                   f"sharded by mesh over {world} GPU(s) (LPT), metadata blobs ({blob_bytes} B) gathered to every rank", "l2": "meshes are built back to back; each build streams its own arrays"},
+            "clocks": _clock_summary(clock_samples),
+            "e2e": {"value": tris / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": int(sum(v.nbytes + i.nbytes for v, i in host)), "d2h_bytes_per_step": None},
+            "gpu_launches": int(launches),
+        }))
+    for h in handles:
+        lib.free_geometry(h)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    if WORKLOAD == "C4":
+        return run_scene_batch(args)
     rank, world, local = _dist()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
