@@ -15,9 +15,11 @@ using namespace clodb;
 namespace
 {
 thread_local std::string t_last_error;
-std::mutex g_api_mutex;
+std::mutex g_api_mutex; // guards process-wide state only (initialisation); builds run on per-thread contexts without it
 bool g_initialized = false;
-Workspace g_ws;
+int g_device = 0;
+thread_local Workspace g_ws;
+thread_local bool t_context_ready = false;
 
 int fail(int code, const std::string& message)
 {
@@ -83,14 +85,29 @@ float* upload_positions(const float* positions, size_t vertex_count, size_t stri
 	return dev;
 }
 
+// The calling thread's build context: device selection and its own non-blocking stream (the arenas, scan-chain
+// descriptors and pinned staging of the thread grow on demand).
+void ensure_thread_context()
+{
+	if (t_context_ready)
+		return;
+#ifndef CLODB_EMU
+	CUDA_CHECK(cudaSetDevice(g_device));
+	cudaStream_t s;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	g_stream = s;
+#endif
+	t_context_ready = true;
+}
+
 template <typename F>
 int guarded(F&& body)
 {
-	std::lock_guard<std::mutex> lock(g_api_mutex);
 	if (!g_initialized)
 		return fail(CLODB200_ERR_NO_DEVICE, "clodb200: not initialised (call clodb200_init; a CUDA device is required, there is no CPU path)");
 	try
 	{
+		ensure_thread_context();
 		return body();
 	}
 	catch (const std::exception& e)
@@ -198,11 +215,15 @@ int clodb200_init(int device)
 	e = cudaSetDevice(device);
 	if (e != cudaSuccess)
 		return fail(CLODB200_ERR_NO_DEVICE, std::string("clodb200: cudaSetDevice failed: ") + cudaGetErrorString(e));
-	cudaStream_t s;
-	e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-	if (e != cudaSuccess)
-		return fail(CLODB200_ERR_NO_DEVICE, std::string("clodb200: stream creation failed: ") + cudaGetErrorString(e));
-	g_stream = s;
+	g_device = device;
+	try
+	{
+		ensure_thread_context();
+	}
+	catch (const std::exception& ex)
+	{
+		return fail(CLODB200_ERR_NO_DEVICE, std::string("clodb200: stream creation failed: ") + ex.what());
+	}
 	if (const char* dbg = getenv("CLODB200_SYNC_DEBUG"))
 		g_sync_debug = atoi(dbg);
 #else
@@ -223,9 +244,11 @@ void clodb200_shutdown(void)
 	g_ws.temp.destroy();
 	g_ws.stage.destroy();
 #ifndef CLODB_EMU
-	cudaStreamDestroy(g_stream);
+	if (t_context_ready)
+		cudaStreamDestroy(g_stream);
 	g_stream = 0;
 #endif
+	t_context_ready = false; // contexts of other threads are left to process exit
 	g_initialized = false;
 }
 
@@ -518,7 +541,7 @@ struct DeviceBlock
 	void* ptr;
 	size_t bytes;
 };
-static std::vector<DeviceBlock> g_block_cache;
+static thread_local std::vector<DeviceBlock> g_block_cache;
 
 static void* block_alloc(size_t bytes, std::vector<DeviceBlock>& owned)
 {
@@ -680,7 +703,7 @@ struct CallbackSink : DagSink
 	}
 };
 
-static BuildStats g_last_build_stats;
+static thread_local BuildStats g_last_build_stats;
 
 static size_t build_locked(const clodb200_config& config, const clodb200_device_mesh* dm, DagSink& sink)
 {
@@ -768,7 +791,7 @@ size_t clodb200_buildEx(clodb200_config config, clodb200_mesh mesh, void* output
 	return build_host(config, mesh, output_context, output_callback, nullptr);
 }
 
-static clodb200_record* g_record_pool = nullptr; // one recycled record (buffers keep their capacity between builds)
+static thread_local clodb200_record* g_record_pool = nullptr; // one recycled record (buffers keep their capacity between builds)
 
 static clodb200_record* record_build(const clodb200_config& config, const clodb200_device_mesh* dm, bool keep_indices)
 {
@@ -876,7 +899,7 @@ struct clodb200_device_geometry
 	std::vector<DeviceBlock> allocations;
 };
 
-static clodb200_artifacts* g_artifacts_pool = nullptr; // one recycled result (keeps its pinned page buffer)
+static thread_local clodb200_artifacts* g_artifacts_pool = nullptr; // one recycled result (keeps its pinned page buffer)
 
 static BuilderSettings to_settings(const clodb200_builder_settings* s)
 {
@@ -1216,7 +1239,7 @@ int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char*
 }
 
 #ifndef CLODB_EMU
-static cudaEvent_t g_timer_start = nullptr, g_timer_stop = nullptr;
+static thread_local cudaEvent_t g_timer_start = nullptr, g_timer_stop = nullptr;
 #endif
 
 void clodb200_timerStart(void)

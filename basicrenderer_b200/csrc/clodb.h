@@ -126,7 +126,7 @@ struct SimplifyStats
 	u32 window_extensions = 0;
 	u32 sloppy_groups = 0;
 };
-extern SimplifyStats g_simplify_stats;
+extern thread_local SimplifyStats g_simplify_stats;
 // One meshopt_simplifyWithAttributes(Sparse|ErrorAbsolute|Permissive) per group, all groups batched. gtri holds each
 // group's merged index list back to back; locks is the per-vertex lock byte array of the level.
 SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host, u32 group_count, const DeviceMesh& mesh, const u32* global_remap, const u8* locks, const Config& config, Workspace& ws);

@@ -191,7 +191,7 @@ struct ScanChain
 	u32 epoch = 0;
 };
 static const int SCAN_CHAIN_VALUE_BYTES = 32;
-extern ScanChain g_scan_chain;
+extern thread_local ScanChain g_scan_chain;
 void scan_chain_reserve(size_t tiles);
 
 // returns the next epoch (never 0 in the low 30 bits, so stale or zeroed descriptors never match)

@@ -6,13 +6,13 @@
 namespace clodb
 {
 
-stream_t g_stream = 0;
-uint64_t g_launches = 0;
+thread_local stream_t g_stream = 0;
+thread_local uint64_t g_launches = 0;
 int g_sync_debug = 0;
-int g_profile = 0;
+thread_local int g_profile = 0;
 
 #ifdef CLODB_EMU
-size_t emu_tid = 0;
+thread_local size_t emu_tid = 0;
 int emu_reverse = 0;
 
 void* dev_malloc(size_t bytes)
@@ -69,8 +69,8 @@ void dev_d2h_async_wait()
 #else
 namespace
 {
-cudaStream_t g_copy_stream = nullptr;
-cudaEvent_t g_copy_ready = nullptr, g_copy_done = nullptr;
+thread_local cudaStream_t g_copy_stream = nullptr;
+thread_local cudaEvent_t g_copy_ready = nullptr, g_copy_done = nullptr;
 void ensure_copy_stream()
 {
 	if (g_copy_stream)
@@ -137,8 +137,8 @@ void dev_memset(void* p, int value, size_t bytes)
 // staging copy. Larger transfers keep the plain path.
 static const size_t SMALL_XFER = 1024;
 static const size_t RING_SLOTS = 512;
-static char* g_pinned_ring = nullptr; // RING_SLOTS upload slots + one read-back slot
-static size_t g_ring_next = 0;
+static thread_local char* g_pinned_ring = nullptr; // RING_SLOTS upload slots + one read-back slot
+static thread_local size_t g_ring_next = 0;
 
 static char* pinned_ring()
 {
@@ -214,8 +214,8 @@ struct ProfileSpan
 	cudaEvent_t start, stop;
 	size_t threads;
 };
-std::vector<ProfileSpan> g_spans;
-std::vector<cudaEvent_t> g_event_pool;
+thread_local std::vector<ProfileSpan> g_spans;
+thread_local std::vector<cudaEvent_t> g_event_pool;
 
 cudaEvent_t take_event()
 {
@@ -296,7 +296,7 @@ std::string profile_report()
 #endif
 
 #ifndef CLODB_EMU
-ScanChain g_scan_chain;
+thread_local ScanChain g_scan_chain;
 
 void scan_chain_reserve(size_t tiles)
 {

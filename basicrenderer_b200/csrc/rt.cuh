@@ -41,7 +41,7 @@ struct Error : std::runtime_error
 #define HOSTDEVFN static inline
 #define CONSTANT static const
 
-extern size_t emu_tid;
+extern thread_local size_t emu_tid;
 extern int emu_reverse;
 #define GTID (::clodb::emu_tid)
 
@@ -210,12 +210,15 @@ typedef cudaStream_t stream_t;
 	} while (0)
 #endif
 
-extern stream_t g_stream;
-extern uint64_t g_launches;
+// Build context of the calling host thread: every thread that calls into the library gets its own stream, launch counter,
+// workspace arenas, scan-chain descriptors and pinned staging (capi.cu creates them on first use), so independent meshes can
+// be built concurrently from several threads of one process (scene batches of small meshes are launch-latency bound).
+extern thread_local stream_t g_stream;
+extern thread_local uint64_t g_launches;
 extern int g_sync_debug;
 
 // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg); off by default
-extern int g_profile;
+extern thread_local int g_profile;
 void profile_mark(const char* kernel_name, int end, size_t threads);
 // persistent kernels: replace the thread count of the span just recorded by the number of work items it processed
 void profile_set_last_work(size_t items);

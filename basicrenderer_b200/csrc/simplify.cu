@@ -2221,7 +2221,7 @@ static void build_adjacency(const u32* idx, size_t corners, const u32* remap, u3
 		LAUNCH(k_adj_sort, vertex_count, adj_off, adj_corner, vertex_count);
 }
 
-SimplifyStats g_simplify_stats;
+thread_local SimplifyStats g_simplify_stats;
 
 SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host, u32 G, const DeviceMesh& mesh, const u32* global_remap, const u8* locks, const Config& config, Workspace& ws)
 {
