@@ -63,10 +63,16 @@ typedef struct clodb200_config
 } clodb200_config;
 
 const char* clodb200_last_error(void);
-/* Selects the CUDA device for this process (one process per GPU) and creates the build stream. */
+/* Selects the CUDA device for this process (one process per GPU). Threading: every host thread that calls the library gets
+ * its own build context on first use (CUDA stream, device arenas, pinned staging), so independent meshes may be built
+ * concurrently from several threads — the reference builds one primitive per worker thread the same way
+ * (Import/GlTFGeometryExtractor.cpp:1349, Import/USDGeometryExtractor.cpp:945-961). A handle (uploaded mesh/geometry,
+ * record, artifacts) may be used by any thread, by one thread at a time; an artifacts/record handle should be freed by the
+ * thread that built it (it is recycled for that thread's next build). clodb200_launch_count and the timer/profile calls
+ * refer to the calling thread's context. */
 int clodb200_init(int device);
 void clodb200_shutdown(void);
-/* Kernel launches issued by this library since clodb200_init (bench.py's gpu_launches). */
+/* Kernel launches issued by the calling thread since it first used the library (bench.py's gpu_launches). */
 uint64_t clodb200_launch_count(void);
 
 /* clodDefaultConfig(max_triangles) followed by the BasicRenderer overrides (ClusterLODUtilities.cpp:5426-5460). */
