@@ -1,0 +1,36 @@
+"""bench.py's reference arm runs without a GPU (it times the compiled reference on the host cores): check the JSON line
+the driver parses. The CUDA arm needs a device and is exercised on the GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line(oracle):
+    from oracle import clodfull
+
+    if not clodfull.available(True):
+        import pytest
+
+        pytest.skip("reference L3 builder not built")
+    env = dict(os.environ, CLODB200_REF_GRID="120")  # bounded sample: 28 800 triangles
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], env=env, text=True)
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mtris/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_bench_byte_model_covers_the_kernels_it_can_report():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for k in ("k_sa_chained", "k_wave_rounds", "k_partition_chained", "k_pivot_large", "k_rs_scatter<K>"):
+        assert bench.KERNEL_BYTES_PER_THREAD[k] > 0
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_dram_traffic.json")))
+    assert set(traffic["kernels"]) <= set(bench.KERNEL_BYTES_PER_THREAD)
