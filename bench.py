@@ -82,6 +82,21 @@ except Exception:
     pass
 
 
+def _kernel_table(rows, peak_gbs, limit=10):
+    """Top kernels of one profiled step: time, launches and, where DESIGN.md has a byte model for the kernel, the algorithmic
+    GB/s and its fraction of the measured HBM peak. rows: (kernel, launches, total_ms, total_threads_or_items)."""
+    out = []
+    for name, launches, ms, threads in rows[:limit]:
+        entry = {"kernel": name, "launches": int(launches), "ms": round(float(ms), 3)}
+        bpt = KERNEL_BYTES_PER_THREAD.get(name)
+        if bpt and ms > 0:
+            gbs = bpt * threads / (ms * 1e-3) / 1e9
+            entry["algorithmic_gbs"] = round(gbs, 1)
+            entry["frac"] = round(gbs / peak_gbs, 4)
+        out.append(entry)
+    return out
+
+
 def _sample_clocks(stop_event, out):
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     idx = os.environ.get("LOCAL_RANK", "0")
@@ -371,7 +386,7 @@ def run_ours(args):
             "kernel_share_of_step": top[2] / total_kernel_ms if total_kernel_ms else None,
             "launches": top[1],
             "avg_launch_us": top[2] * 1e3 / max(1, top[1]),
-            "top_kernels": [{"kernel": r[0], "launches": r[1], "ms": round(r[2], 3)} for r in rows[:8]],
+            "top_kernels": _kernel_table(rows, peak),
         }
 
         cpu = cpu_baseline_sample()

@@ -34,3 +34,19 @@ def test_bench_byte_model_covers_the_kernels_it_can_report():
         assert bench.KERNEL_BYTES_PER_THREAD[k] > 0
     traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_dram_traffic.json")))
     assert set(traffic["kernels"]) <= set(bench.KERNEL_BYTES_PER_THREAD)
+
+
+def test_kernel_table_on_the_committed_event_profile():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    rows = []
+    for line in open(os.path.join(ROOT, "profiles", "r01_c2_kernel_events_v16.csv")).read().splitlines()[1:]:
+        name, count, ms, threads = line.rsplit(",", 3)
+        rows.append((name, int(count), float(ms), int(threads)))
+    table = bench._kernel_table(rows, 6515.4)
+    assert len(table) == 10 and table[0]["kernel"] == rows[0][0]
+    by_name = {t["kernel"]: t for t in table}
+    assert 0.3 < by_name["k_sa_chained"]["frac"] < 0.7  # 8 positions x 44 B per thread
+    assert by_name["k_wave_rounds"]["frac"] < 0.05  # latency bound, reported as such
+    json.dumps(table)
