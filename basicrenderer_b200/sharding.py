@@ -82,8 +82,9 @@ def gather_metadata(mesh_ids: Sequence[int], blobs: Sequence[bytes], device=None
 
 
 def dag_summary_blob(rec) -> bytes:
-    """Compact per-mesh metadata of a recorded build: per group {depth, simplified bounds[5], cluster count}. (The
-    reference's full metadata blob — CLodCache.cpp:169-207 — belongs to the L3 builder rows still to come.)"""
+    """Compact per-mesh summary of a recorded DAG build (clodBuildEx level): per group {depth, simplified bounds[5], cluster
+    count}. The artifacts path gathers the reference's full metadata blob instead (ClodLib.serialize_metadata,
+    CLodCache.cpp:169-207)."""
     depth = np.asarray(rec.group_depth, np.int32)
     simp = np.asarray(rec.group_simplified, np.float32).reshape(-1, 5)
     counts = np.diff(np.asarray(rec.group_cluster_offsets, np.uint32)).astype(np.uint32)
