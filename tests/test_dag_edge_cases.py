@@ -1,0 +1,116 @@
+"""Whole-DAG parity on awkward inputs, against the compiled reference (clodBuildEx of clusterlod.h + meshoptimizer): degenerate
+and zero-area triangles, unwelded triangle soup, disconnected components, non-manifold edges, tiny meshes, fully locked
+meshes, position-only meshes. The meshes are small enough that every level is one group, so the callback stream must equal
+the reference's bit for bit. Runs on the host emulation of the kernel sources (stage logic; the CUDA library runs the same
+sources and is compared with the reference on the regular meshes by test_dag.py / test_stages.py with -m gpu)."""
+import numpy as np
+import pytest
+
+from basicrenderer_b200 import invariants, meshgen
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from basicrenderer_b200 import build
+    from basicrenderer_b200.api import ClodLib
+
+    return ClodLib(build.build_emu())
+
+
+def _soup(m):
+    """every triangle gets its own three vertices (positions repeat: the position remap has to weld them)"""
+    idx = m.indices.reshape(-1)
+    return m.positions[idx].copy(), m.normals[idx].copy(), np.arange(idx.size, dtype=np.uint32)
+
+
+def _cases():
+    g = meshgen.grid(24, seed=2)
+    out = {}
+    out["grid24"] = (g.positions, g.normals, g.indices, None)
+    # degenerate index triples and zero-area (collinear) triangles sprinkled in
+    idx = g.indices.reshape(-1, 3).copy()
+    extra = np.array([[0, 0, 1], [5, 5, 5], [0, 1, 2], [10, 11, 12], [3, 4, 3]], np.uint32)  # (0,1,2) and (10,11,12) lie on a grid row
+    out["degenerate"] = (g.positions, g.normals, np.concatenate([idx[:300], extra, idx[300:]]).reshape(-1), None)
+    out["soup"] = _soup(meshgen.grid(12, seed=4)) + (None,)
+    # two components far apart
+    a, b = meshgen.grid(14, seed=5), meshgen.icosphere(5)
+    out["two_components"] = (np.concatenate([a.positions, b.positions + np.float32(10.0)]), np.concatenate([a.normals, b.normals]),
+                             np.concatenate([a.indices.reshape(-1), b.indices.reshape(-1) + a.positions.shape[0]]).astype(np.uint32), None)
+    # non-manifold fin: a third triangle on an interior edge, plus one flipped copy of an existing triangle
+    fin_v = np.array([[0.5, 0.5, 0.4]], np.float32)
+    t0 = g.indices.reshape(-1, 3)[200]
+    fin = np.array([[t0[0], t0[1], g.positions.shape[0]], [t0[0], t0[2], t0[1]]], np.uint32)
+    out["non_manifold"] = (np.concatenate([g.positions, fin_v]), np.concatenate([g.normals, np.array([[0, 0, 1]], np.float32)]),
+                           np.concatenate([g.indices.reshape(-1, 3), fin]).reshape(-1), None)
+    for n, name in ((1, "one_triangle"), (2, "two_triangles"), (129, "just_over_one_meshlet")):
+        out[name] = (g.positions, g.normals, g.indices.reshape(-1, 3)[:n].reshape(-1).copy(), None)
+    out["all_locked"] = (g.positions, g.normals, g.indices, np.ones(g.positions.shape[0], np.uint8))
+    out["position_only"] = (g.positions, None, g.indices, None)
+    # anisotropic scale and a large offset (float cancellation in the quadrics and the sphere fits)
+    out["scaled_offset"] = (g.positions * np.array([1000.0, 0.001, 1.0], np.float32) + np.float32(1.0e5), g.normals, g.indices, None)
+    # random triangles over random points: non-manifold almost everywhere, many complex/locked vertex kinds
+    rng = np.random.default_rng(11)
+    pts = rng.random((150, 3)).astype(np.float32)
+    nrm = rng.standard_normal((150, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    tri = rng.integers(0, 150, (400, 3)).astype(np.uint32)
+    out["random_triangles"] = (pts, nrm, tri.reshape(-1), None)
+    # a fan of 300 triangles around one vertex (valence far above the meshlet size)
+    k = 300
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    ring = np.stack([np.cos(ang), np.sin(ang), 0.05 * np.sin(7 * ang)], axis=1).astype(np.float32)
+    fan_p = np.concatenate([np.zeros((1, 3), np.float32), ring])
+    fan_n = np.tile(np.array([[0, 0, 1]], np.float32), (k + 1, 1))
+    fan_i = np.stack([np.zeros(k, np.uint32), 1 + np.arange(k, dtype=np.uint32), 1 + (np.arange(k, dtype=np.uint32) + 1) % k], axis=1)
+    out["high_valence_fan"] = (fan_p, fan_n, fan_i.reshape(-1), None)
+    return out
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_edge_case_dag_equals_reference(emu, oracle, name):
+    positions, normals, indices, vertex_lock = CASES[name]
+    positions = np.ascontiguousarray(positions, np.float32)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    kw = dict(attributes=normals, attribute_weights=np.ones(3, np.float32), protect_mask=7) if normals is not None else {}
+    if vertex_lock is not None:
+        kw["vertex_lock"] = vertex_lock
+    rec = emu.build_dag(positions, indices, **kw)
+    invariants.check_dag(rec, positions, indices, remap=oracle.position_remap(positions))
+    if vertex_lock is not None:
+        # the oracle's dump driver has no vertex_lock input: with every vertex locked nothing can collapse, so every group
+        # is stuck (simplified > 0.85 x input, clusterlod.h:723) and the DAG ends at depth 0 with FLT_MAX errors
+        assert rec.levels == 1 and np.all(rec.group_simplified[:, 4] == invariants.FLT_MAX)
+        return
+    kw.pop("vertex_lock", None)
+    ref = oracle.dag_build(positions, indices, **kw)
+    if any(len(ref.level(l, "group_offsets")) != 2 for l in range(ref.num_levels)):
+        pytest.skip("reference uses several groups on some level")
+    for ours, theirs in (("group_depth", "out.group_depth"), ("group_cluster_offsets", "out.group_cluster_offsets"), ("cluster_refined", "out.cluster_refined"),
+                         ("cluster_indices", "out.cluster_indices"), ("cluster_vertex_count", "out.cluster_vertex_count"), ("cluster_bounds", "out.cluster_bounds"),
+                         ("group_simplified", "out.group_simplified")):
+        a, b = np.asarray(getattr(rec, ours)), np.asarray(ref.get(theirs))
+        assert a.shape == b.reshape(a.shape).shape and np.array_equal(a, b.reshape(a.shape)), f"{name}: {ours} differs from the reference"
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n][1] is not None and CASES[n][3] is None])
+def test_edge_case_artifacts_equal_the_unmodified_reference_builder(emu, name):
+    """The whole outer call (BuildClusterLODArtifactsFromGeometry with the reference's OWN clodBuildEx) against ours: every
+    table and every page byte, on inputs where the grouping is forced."""
+    from oracle import clodfull
+
+    from basicrenderer_b200 import artifacts as art
+    from test_artifacts import _assert_identical  # tests/ is on sys.path under pytest's rootdir conftest
+
+    if not clodfull.available(True):
+        pytest.skip("reference L3 builder not built")
+    positions, normals, indices, _ = CASES[name]
+    v = art.interleave(np.ascontiguousarray(positions, np.float32), normals)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    ref = clodfull.build(v, indices)
+    ours = emu.build_artifacts(v, indices, art.VERTEX_NORMALS)
+    if np.bincount(np.asarray(ref.groups["depth"])).max() > 1:
+        pytest.skip("reference uses several groups on some level")
+    _assert_identical(ref, ours)
