@@ -37,6 +37,31 @@ void ensure_workspace(size_t persist_bytes, size_t temp_bytes)
 	g_ws.temp.release(0);
 }
 
+// Runs `attempt` again with a larger slab while it fails with ArenaExhausted and `may_retry()` allows it (nothing has been
+// handed to the caller yet). ensure_workspace never shrinks a slab, so the growth sticks for the retry and later builds.
+template <typename Attempt, typename MayRetry>
+auto with_arena_growth(Attempt&& attempt, MayRetry&& may_retry) -> decltype(attempt())
+{
+	for (int tries = 0;; ++tries)
+	{
+		try
+		{
+			return attempt();
+		}
+		catch (const ArenaExhausted& e)
+		{
+			if (tries >= 16 || !may_retry())
+				throw;
+			Arena& slab = e.arena == &g_ws.persist ? g_ws.persist : g_ws.temp;
+			if (e.arena != &g_ws.persist && e.arena != &g_ws.temp)
+				throw;
+			size_t want = std::max(slab.capacity * 2, e.need * 2);
+			dev_sync();
+			slab.init(want);
+		}
+	}
+}
+
 Config to_config(const clodb200_config* c)
 {
 	Config r;
@@ -688,6 +713,7 @@ struct CallbackSink : DagSink
 	void* context;
 	clodb200_outputEx callback_ex;
 	clodb200_output callback;
+	size_t delivered = 0; // groups handed to the caller so far (a build that has delivered anything is not restarted)
 
 	int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t task_index) override
 	{
@@ -695,6 +721,7 @@ struct CallbackSink : DagSink
 		clodb200_group g;
 		memcpy(&g, &group, sizeof(g));
 		const clodb200_cluster* c = reinterpret_cast<const clodb200_cluster*>(clusters);
+		delivered++;
 		if (callback_ex)
 			return callback_ex(context, g, c, cluster_count, task_index, 0);
 		if (callback)
@@ -709,10 +736,12 @@ static size_t build_locked(const clodb200_config& config, const clodb200_device_
 {
 	size_t T = dm->index_count / 3;
 	size_t V = dm->mesh.vertex_count;
-	size_t scale_temp = 640, scale_persist = 96;
+	size_t scale_temp = 640, scale_persist = 96, base_temp = 64u << 20;
 	if (const char* e = getenv("CLODB200_TEMP_BYTES_PER_TRI"))
 		scale_temp = size_t(atoll(e));
-	ensure_workspace(T * scale_persist + V * 32 + (64u << 20), T * scale_temp + V * 16 + (64u << 20));
+	if (const char* e = getenv("CLODB200_TEMP_BYTES_BASE")) // tests start from a starved slab to exercise the growth path
+		base_temp = size_t(atoll(e));
+	ensure_workspace(T * scale_persist + V * 32 + (64u << 20), T * scale_temp + V * 16 + base_temp);
 	return build_dag(to_config(&config), dm->mesh, dm->indices, dm->index_count, g_ws, sink, g_last_build_stats);
 }
 
@@ -727,7 +756,7 @@ size_t clodb200_meshBuildEx(clodb200_config config, const clodb200_device_mesh* 
 		sink.callback_ex = output_callback;
 		sink.callback = nullptr;
 		t_last_error.clear();
-		result = build_locked(config, mesh, sink);
+		result = with_arena_growth([&]() { return build_locked(config, mesh, sink); }, [&]() { return sink.delivered == 0; });
 		return CLODB200_OK;
 	});
 	return status == CLODB200_OK ? result : 0;
@@ -768,7 +797,7 @@ static size_t build_host(clodb200_config config, clodb200_mesh mesh, void* outpu
 			sink.context = output_context;
 			sink.callback_ex = cb_ex;
 			sink.callback = cb;
-			result = build_locked(config, dm, sink);
+			result = with_arena_growth([&]() { return build_locked(config, dm, sink); }, [&]() { return sink.delivered == 0; });
 		}
 		catch (...)
 		{
@@ -793,7 +822,7 @@ size_t clodb200_buildEx(clodb200_config config, clodb200_mesh mesh, void* output
 
 static thread_local clodb200_record* g_record_pool = nullptr; // one recycled record (buffers keep their capacity between builds)
 
-static clodb200_record* record_build(const clodb200_config& config, const clodb200_device_mesh* dm, bool keep_indices)
+static clodb200_record* record_build_once(const clodb200_config& config, const clodb200_device_mesh* dm, bool keep_indices)
 {
 	clodb200_record* rec = g_record_pool ? g_record_pool : new clodb200_record();
 	g_record_pool = nullptr;
@@ -819,6 +848,11 @@ static clodb200_record* record_build(const clodb200_config& config, const clodb2
 		throw;
 	}
 	return rec;
+}
+
+static clodb200_record* record_build(const clodb200_config& config, const clodb200_device_mesh* dm, bool keep_indices)
+{
+	return with_arena_growth([&]() { return record_build_once(config, dm, keep_indices); }, []() { return true; });
 }
 
 clodb200_record* clodb200_meshBuildRecorded(clodb200_config config, const clodb200_device_mesh* mesh, int keep_indices)
@@ -1043,16 +1077,18 @@ static clodb200_artifacts* take_artifacts()
 	return a;
 }
 
-static clodb200_artifacts* build_artifacts_locked(const clodb200_device_geometry* dg)
+static clodb200_artifacts* build_artifacts_once(const clodb200_device_geometry* dg)
 {
 	clodb200_artifacts* a = take_artifacts();
 	try
 	{
 		size_t T = dg->geometry.index_count / 3, V = dg->geometry.vertex_count;
-		size_t scale_temp = 640, scale_persist = 96;
+		size_t scale_temp = 640, scale_persist = 96, base_temp = 64u << 20;
 		if (const char* e = getenv("CLODB200_TEMP_BYTES_PER_TRI"))
 			scale_temp = size_t(atoll(e));
-		size_t temp_bytes = T * scale_temp + V * 16 + (64u << 20);
+		if (const char* e = getenv("CLODB200_TEMP_BYTES_BASE"))
+			base_temp = size_t(atoll(e));
+		size_t temp_bytes = T * scale_temp + V * 16 + base_temp;
 		const DeviceGeometry& geo = dg->geometry;
 		if (geo.generated_tangents4)
 			temp_bytes = std::max(temp_bytes, mikk_temp_bytes(V, geo.index_count));
@@ -1073,6 +1109,11 @@ static clodb200_artifacts* build_artifacts_locked(const clodb200_device_geometry
 		throw;
 	}
 	return a;
+}
+
+static clodb200_artifacts* build_artifacts_locked(const clodb200_device_geometry* dg)
+{
+	return with_arena_growth([&]() { return build_artifacts_once(dg); }, []() { return true; });
 }
 
 clodb200_builder_settings clodb200_defaultBuilderSettings(void)

@@ -248,6 +248,20 @@ void dev_d2h_async(void* dst_host_pinned, const void* src, size_t bytes);
 void dev_d2h_async_wait();
 
 // ---- stack arena: all per-build temporaries come from one cudaMalloc'd slab (no allocator calls inside the loop) -----
+struct Arena;
+// Thrown by Arena::alloc_bytes. The slabs are sized from the triangle count; inputs whose adjacency is far denser than a
+// surface's (triangle soups sharing each vertex among dozens of clusters) can need more, so the C-ABI build entry points
+// grow the slab named here and run the (deterministic, side-effect free until it returns) build again.
+struct ArenaExhausted : Error
+{
+	const Arena* arena;
+	size_t need;
+	ArenaExhausted(const Arena* a, size_t need_bytes, const std::string& what)
+	    : Error(what), arena(a), need(need_bytes)
+	{
+	}
+};
+
 struct Arena
 {
 	char* base = nullptr;
@@ -285,7 +299,7 @@ struct Arena
 			return debug_alloc(aligned, bytes);
 		}
 		if (aligned + bytes > capacity)
-			throw Error("clodb200: device arena exhausted (need " + std::to_string(aligned + bytes) + " of " + std::to_string(capacity) + " bytes)");
+			throw ArenaExhausted(this, aligned + bytes, "clodb200: device arena exhausted (need " + std::to_string(aligned + bytes) + " of " + std::to_string(capacity) + " bytes)");
 		offset = aligned + bytes;
 		if (offset > high_water)
 			high_water = offset;
