@@ -114,3 +114,18 @@ def test_edge_case_artifacts_equal_the_unmodified_reference_builder(emu, name):
     if np.bincount(np.asarray(ref.groups["depth"])).max() > 1:
         pytest.skip("reference uses several groups on some level")
     _assert_identical(ref, ours)
+
+
+def test_dense_adjacency_soup_grows_the_slab_and_keeps_the_invariants(emu, oracle):
+    """20 000 random triangles over 1 000 points: every vertex is shared by ~60 triangles spread over dozens of meshlets, so the
+    cluster adjacency (pairs of clusters sharing a vertex) is two orders of magnitude denser than a surface's and does not fit
+    the slab sized from the triangle count; the build grows it and starts again (capi.cu with_arena_growth). The reference
+    itself needs minutes on this input, so only the invariants are checked."""
+    rng = np.random.default_rng(3)
+    pts = rng.random((1000, 3)).astype(np.float32)
+    nrm = rng.standard_normal((1000, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    tri = rng.integers(0, 1000, (20000, 3)).astype(np.uint32).reshape(-1)
+    rec = emu.build_dag(pts, tri, attributes=nrm, attribute_weights=np.ones(3, np.float32), protect_mask=7)
+    stats = invariants.check_dag(rec, pts, tri, remap=oracle.position_remap(pts))
+    assert stats[0]["triangles"] == 20000 and rec.total_clusters >= 20000 // 128
