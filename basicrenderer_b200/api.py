@@ -83,7 +83,7 @@ OUTPUT_EX = C.CFUNCTYPE(C.c_int, C.c_void_p, Group, C.POINTER(Cluster), C.c_size
 _RECORD_DTYPES = {
     "group_depth": np.int32, "group_simplified": np.float32, "group_cluster_offsets": np.uint32, "cluster_refined": np.int32,
     "cluster_bounds": np.float32, "cluster_vertex_count": np.uint32, "cluster_index_offsets": np.uint64, "cluster_indices": np.uint32,
-    "level_triangles": np.uint32, "level_clusters": np.uint32, "level_groups": np.uint32, "stats": np.uint64,
+    "level_triangles": np.uint32, "level_clusters": np.uint32, "level_groups": np.uint32, "level_passes": np.uint32, "level_sloppy": np.uint32, "stats": np.uint64,
 }
 
 

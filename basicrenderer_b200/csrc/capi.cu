@@ -839,6 +839,8 @@ static clodb200_record* record_build_once(const clodb200_config& config, const c
 		rec->append<u32>("level_triangles", st.level_triangles.data(), st.level_triangles.size());
 		rec->append<u32>("level_clusters", st.level_clusters.data(), st.level_clusters.size());
 		rec->append<u32>("level_groups", st.level_groups.data(), st.level_groups.size());
+		rec->append<u32>("level_passes", st.level_passes.data(), st.level_passes.size());
+		rec->append<u32>("level_sloppy", st.level_sloppy.data(), st.level_sloppy.size());
 		u64 stats[8] = {u64(clusters), st.levels, st.groups, st.simplified_triangles, st.d2h_bytes, st.simplify_passes, st.simplify_rounds, g_launches};
 		rec->append<u64>("stats", stats, 8);
 	}

@@ -230,6 +230,8 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		SimplifyOutput simp = simplify_groups(gtri, group_tri_offset_host.data(), G, mesh, remap, locks, config, ws);
 		double t_simplify = clock.lap();
 		stats.simplify_passes += g_simplify_stats.passes;
+		stats.level_passes.push_back(g_simplify_stats.passes);
+		stats.level_sloppy.push_back(g_simplify_stats.sloppy_groups);
 		stats.simplify_rounds += g_simplify_stats.rounds;
 
 		std::vector<u32> simp_offset = dev_download(simp.group_tri_offset, size_t(G) + 1);
@@ -338,6 +340,8 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		stats.level_triangles.push_back(level.triangle_count);
 		stats.level_clusters.push_back(1);
 		stats.level_groups.push_back(1);
+		stats.level_passes.push_back(0);
+		stats.level_sloppy.push_back(0);
 		GroupSet last;
 		last.group_count = 1;
 		last.cluster_count = 1;

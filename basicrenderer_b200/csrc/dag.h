@@ -53,6 +53,7 @@ struct BuildStats
 	u32 simplify_passes = 0;
 	u32 simplify_rounds = 0;
 	std::vector<u32> level_triangles, level_clusters, level_groups;
+	std::vector<u32> level_passes, level_sloppy; // edge-collapse passes / groups sent through the sloppy fallback, per level
 };
 
 size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indices_dev, size_t index_count, Workspace& ws, DagSink& sink, BuildStats& stats);

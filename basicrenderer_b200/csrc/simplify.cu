@@ -1288,11 +1288,14 @@ KERNEL k_window_init(GroupState* groups, u32 G)
 	gs.win_end = gs.cand_begin + (w < gs.cand_count ? w : gs.cand_count);
 }
 
-KERNEL k_wave_window(const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_group, const GroupState* __restrict__ groups, u32* list, u32* counter, u32 cand_total)
+// Only UNDECIDED candidates are listed: when one group extends its window, the windows of the other groups are unchanged
+// and everything inside them has been decided by the previous run; running a decided candidate through the decide step
+// again would find its own locks and relabel a performed collapse as locked.
+KERNEL k_wave_window(const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_group, const GroupState* __restrict__ groups, const u8* __restrict__ status, u32* list, u32* counter, u32 cand_total)
 {
 	size_t kk = GTID;
 	bool take = false;
-	if (kk < cand_total)
+	if (kk < cand_total && status[kk] == Status_Undecided)
 	{
 		const GroupState& gs = groups[cand_group[sorted_cand[kk]]];
 		take = u32(kk) >= gs.win_begin && u32(kk) < gs.win_end;
@@ -2446,7 +2449,7 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		{
 			// ---- wavefront over the current windows
 			dev_memset(wave_state, 0, 2 * sizeof(u32));
-			LAUNCH(k_wave_window, (size_t(cand_total) + 31) / 32 * 32, sort_val, cand_group, groups, wave_list[0], wave_state, cand_total);
+			LAUNCH(k_wave_window, (size_t(cand_total) + 31) / 32 * 32, sort_val, cand_group, groups, status, wave_list[0], wave_state, cand_total);
 #ifdef CLODB_EMU
 			u32 listed = dev_read(wave_state);
 			for (u32 r = 0; listed != 0; )

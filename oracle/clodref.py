@@ -81,6 +81,8 @@ def lib():
         _lib.clodref_simplify.argtypes = [C.POINTER(ClodConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
         _lib.clodref_dag_build_mt.restype = C.c_size_t
         _lib.clodref_dag_build_mt.argtypes = [C.POINTER(ClodConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint]
+        _lib.clodref_dag_build_stats.restype = C.c_void_p
+        _lib.clodref_dag_build_stats.argtypes = [C.POINTER(ClodConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint]
         _lib.meshopt_computeClusterBounds.restype = None  # struct return handled by wrapper below
     return _lib
 
@@ -98,6 +100,8 @@ _BLOB_DTYPES = {
     "out.group_depth": np.int32, "out.group_simplified": np.float32, "out.group_cluster_offsets": np.uint32,
     "out.cluster_refined": np.int32, "out.cluster_bounds": np.float32, "out.cluster_vertex_count": np.uint32,
     "out.cluster_indices": np.uint32, "out.cluster_index_offsets": np.uint32,
+    "stats.level_groups": np.uint32, "stats.level_clusters": np.uint32, "stats.level_triangles": np.uint32, "stats.level_sloppy": np.uint32,
+    "stats.level_max_error": np.float32,
 }
 
 
@@ -180,6 +184,26 @@ def dag_build_timed(positions, indices, attributes=None, attribute_weights=None,
         attribute_weights = np.ascontiguousarray(attribute_weights, dtype=np.float32)
         acount, astride = attribute_weights.size, attributes.shape[1] * 4
     return lib().clodref_dag_build_mt(C.byref(cfg), _ptr(indices), indices.size, _ptr(positions), positions.shape[0], 12, _ptr(attributes), astride, _ptr(attribute_weights), acount, protect_mask, threads)
+
+
+def dag_build_stats(positions, indices, attributes=None, attribute_weights=None, protect_mask=0, threads=None, config=None) -> dict:
+    """The reference's clodBuildEx (iteration tasks on `threads` host threads, default all) reduced to per-depth statistics of
+    its callback stream: groups, clusters, triangles, max finite group error and sloppy-fallback calls per depth."""
+    cfg = config or builder_config()
+    positions = np.ascontiguousarray(positions, dtype=np.float32)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    acount = astride = 0
+    if attributes is not None:
+        attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+        attribute_weights = np.ascontiguousarray(attribute_weights, dtype=np.float32)
+        acount, astride = attribute_weights.size, attributes.shape[1] * 4
+    threads = threads or os.cpu_count() or 1
+    h = lib().clodref_dag_build_stats(C.byref(cfg), _ptr(indices), indices.size, _ptr(positions), positions.shape[0], 12, _ptr(attributes), astride, _ptr(attribute_weights), acount, protect_mask, threads)
+    d = Dag(h)
+    out = {k.split(".", 1)[1]: d.get(k) for k in ("stats.level_groups", "stats.level_clusters", "stats.level_triangles", "stats.level_sloppy", "stats.level_max_error")}
+    out["total_clusters"] = d.cluster_count
+    d.close()
+    return out
 
 
 def position_remap(positions: np.ndarray) -> np.ndarray:

@@ -14,8 +14,16 @@
 //                            The recorded callback stream must equal clodref_dag_build's (tests/test_oracle.py).
 // Results are returned as named raw blobs (clodref_blob_get).
 #include <meshoptimizer.h>
+
+// Observation hook, not a modification: inside the reference's clusterlod.h the one call of meshopt_simplifySloppy (the
+// fallback of clod::simplify, clusterlod.h:591) is routed through a forwarding wrapper that counts calls, so tests can
+// compare how many groups of a level needed the fallback. The wrapper calls the real, unmodified function.
+extern "C" size_t clodref_counted_simplifySloppy(unsigned int* destination, const unsigned int* indices, size_t index_count, const float* vertex_positions, size_t vertex_count, size_t vertex_positions_stride,
+    const unsigned char* vertex_lock, size_t target_index_count, float target_error, float* result_error);
+#define meshopt_simplifySloppy clodref_counted_simplifySloppy
 #define CLUSTERLOD_IMPLEMENTATION
 #include <ThirdParty/meshoptimizer/clusterlod.h>
+#undef meshopt_simplifySloppy
 
 #include <cstdint>
 #include <cstring>
@@ -221,6 +229,19 @@ static void mtIterate(void* iteration_context, void* output_context, int, size_t
 }
 
 unsigned int g_clodref_threads = 1;
+static std::atomic<unsigned int> g_sloppy_calls(0);
+
+size_t clodref_counted_simplifySloppy(unsigned int* destination, const unsigned int* indices, size_t index_count, const float* vertex_positions, size_t vertex_count, size_t vertex_positions_stride,
+    const unsigned char* vertex_lock, size_t target_index_count, float target_error, float* result_error)
+{
+	g_sloppy_calls.fetch_add(1);
+	return meshopt_simplifySloppy(destination, indices, index_count, vertex_positions, vertex_count, vertex_positions_stride, vertex_lock, target_index_count, target_error, result_error);
+}
+
+unsigned int clodref_sloppy_calls(void)
+{
+	return g_sloppy_calls.load();
+}
 
 static int discardCallback(void* ctx, clodGroup, const clodCluster*, size_t, size_t, unsigned int)
 {
@@ -237,6 +258,67 @@ size_t clodref_dag_build_mt(const clodConfig* config, const unsigned int* indice
 	parallel.iteration_callback = &mtIterate;
 	int next = 0;
 	return clodBuildEx(*config, mesh, &next, &discardCallback, &parallel);
+}
+
+// The reference's real clodBuildEx on `threads` host threads, keeping only per-depth statistics of the callback stream
+// (no index lists): what the scale-parity tests compare at sizes where a full dump would take minutes.
+//   stats.level_groups / level_clusters / level_triangles (u32 per depth), stats.level_max_error (f32, finite errors only),
+//   stats.level_sloppy (u32: fallback calls while that depth's groups were simplified)
+struct StatsRecorder
+{
+	std::vector<uint32_t> groups, clusters, triangles, sloppy;
+	std::vector<float> max_error;
+	int next_group = 0;
+	unsigned int sloppy_seen = 0;
+
+	void touch(size_t depth)
+	{
+		if (groups.size() <= depth)
+		{
+			groups.resize(depth + 1);
+			clusters.resize(depth + 1);
+			triangles.resize(depth + 1);
+			sloppy.resize(depth + 1);
+			max_error.resize(depth + 1);
+		}
+	}
+
+	static int callback(void* ctx, clodGroup group, const clodCluster* cl, size_t cluster_count, size_t, unsigned int)
+	{
+		StatsRecorder* r = static_cast<StatsRecorder*>(ctx);
+		size_t d = size_t(group.depth);
+		r->touch(d);
+		// all iteration tasks of a depth finish before its first callback (clusterlod.h:884-926)
+		unsigned int now = g_sloppy_calls.load();
+		r->sloppy[d] += now - r->sloppy_seen;
+		r->sloppy_seen = now;
+		r->groups[d]++;
+		r->clusters[d] += uint32_t(cluster_count);
+		for (size_t i = 0; i < cluster_count; ++i)
+			r->triangles[d] += uint32_t(cl[i].index_count / 3);
+		if (group.simplified.error < FLT_MAX && group.simplified.error > r->max_error[d])
+			r->max_error[d] = group.simplified.error;
+		return r->next_group++;
+	}
+};
+
+clodref_handle* clodref_dag_build_stats(const clodConfig* config, const unsigned int* indices, size_t index_count, const float* positions, size_t vertex_count, size_t positions_stride,
+    const float* attributes, size_t attributes_stride, const float* attribute_weights, size_t attribute_count, unsigned int protect_mask, unsigned int threads)
+{
+	clodref_handle* h = new clodref_handle();
+	clodMesh mesh = makeMesh(indices, index_count, positions, vertex_count, positions_stride, attributes, attributes_stride, attribute_weights, attribute_count, protect_mask, NULL);
+	g_clodref_threads = threads;
+	clodBuildParallelConfig parallel = {};
+	parallel.iteration_callback = &mtIterate;
+	StatsRecorder rec;
+	rec.sloppy_seen = g_sloppy_calls.load();
+	h->cluster_count = clodBuildEx(*config, mesh, &rec, &StatsRecorder::callback, &parallel);
+	h->store.put("stats.level_groups", rec.groups);
+	h->store.put("stats.level_clusters", rec.clusters);
+	h->store.put("stats.level_triangles", rec.triangles);
+	h->store.put("stats.level_sloppy", rec.sloppy);
+	h->store.put("stats.level_max_error", rec.max_error);
+	return h;
 }
 
 // Same loop as clodBuildEx (clusterlod.h:792-943) expressed with the reference's own clod:: functions, recording
