@@ -142,6 +142,12 @@ class ClodLib:
         _art.bind(L)
         self._check(L.clodb200_init(device))
 
+    def init(self, device: int = 0):
+        self._check(self._lib.clodb200_init(device))
+
+    def shutdown(self):
+        self._lib.clodb200_shutdown()
+
     def _check(self, status: int):
         if status != 0:
             raise ClodbError(self._lib.clodb200_last_error().decode())

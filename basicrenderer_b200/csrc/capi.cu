@@ -7,6 +7,7 @@
 #include <map>
 #include <algorithm>
 
+#include <atomic>
 #include <mutex>
 #include <functional>
 
@@ -18,8 +19,32 @@ thread_local std::string t_last_error;
 std::mutex g_api_mutex; // guards process-wide state only (initialisation); builds run on per-thread contexts without it
 bool g_initialized = false;
 int g_device = 0;
-thread_local Workspace g_ws;
+// the workspace and the block cache live on the heap behind trivially destructible thread_local pointers: the context owner
+// below releases them from its destructor at thread exit, when other thread_local objects may already have been destroyed
+thread_local Workspace* t_ws = nullptr;
+Workspace& ws_ref()
+{
+	if (!t_ws)
+		t_ws = new Workspace();
+	return *t_ws;
+}
+#define g_ws (ws_ref())
 thread_local bool t_context_ready = false;
+// Bumped by clodb200_shutdown: a thread whose context was created before the last shutdown drops it (streams and slabs may
+// belong to another device) and builds a new one on its next call.
+std::atomic<uint64_t> g_generation{1};
+thread_local uint64_t t_generation = 0;
+void release_thread_context() noexcept;
+// RAII owner of the calling thread's build context: a host thread that builds and then exits gives back its device slabs,
+// pinned staging, streams and cached blocks instead of leaking them until process exit.
+struct ThreadContextOwner
+{
+	~ThreadContextOwner()
+	{
+		release_thread_context();
+	}
+};
+thread_local ThreadContextOwner t_context_owner;
 
 int fail(int code, const std::string& message)
 {
@@ -62,11 +87,31 @@ auto with_arena_growth(Attempt&& attempt, MayRetry&& may_retry) -> decltype(atte
 	}
 }
 
+// clodConfig fields that change the reference's output and are not built here fail loudly instead of being dropped
+// (the struct is layout-identical to clodConfig, so a memcpy'd clodDefaultConfig() arrives with cluster_spatial = false).
+struct UnsupportedConfig : Error
+{
+	explicit UnsupportedConfig(const std::string& what)
+	    : Error(what)
+	{
+	}
+};
+
 Config to_config(const clodb200_config* c)
 {
 	Config r;
 	if (!c)
 		return r;
+	if (!c->cluster_spatial)
+		throw UnsupportedConfig("clodb200: clodConfig::cluster_spatial = false (meshopt_buildMeshletsFlex) is not supported; the reference builder sets cluster_spatial = true (ClusterLODUtilities.cpp:5430)");
+	if (c->simplify_regularize)
+		throw UnsupportedConfig("clodb200: clodConfig::simplify_regularize is not supported");
+	if (c->simplify_fallback_permissive && !c->simplify_permissive)
+		throw UnsupportedConfig("clodb200: clodConfig::simplify_fallback_permissive is not supported (use simplify_permissive)");
+	if (c->simplify_error_edge_limit > 0)
+		throw UnsupportedConfig("clodb200: clodConfig::simplify_error_edge_limit is not supported");
+	if (c->max_vertices == 0 || c->max_vertices > 256 || c->max_triangles == 0 || c->max_triangles > 256 || c->min_triangles > c->max_triangles)
+		throw UnsupportedConfig("clodb200: clodConfig meshlet limits out of range (max_vertices and max_triangles in 1..256, min_triangles <= max_triangles)");
 	r.max_vertices = u32(c->max_vertices);
 	r.min_triangles = u32(c->min_triangles);
 	r.max_triangles = u32(c->max_triangles);
@@ -114,8 +159,12 @@ float* upload_positions(const float* positions, size_t vertex_count, size_t stri
 // descriptors and pinned staging of the thread grow on demand).
 void ensure_thread_context()
 {
-	if (t_context_ready)
+	if (t_context_ready && t_generation == g_generation.load())
 		return;
+	if (t_context_ready)
+		release_thread_context(); // left over from before a shutdown
+	(void)&t_context_owner;       // odr-use: constructs the owner so its destructor runs at thread exit
+	t_generation = g_generation.load();
 #ifndef CLODB_EMU
 	CUDA_CHECK(cudaSetDevice(g_device));
 	cudaStream_t s;
@@ -265,15 +314,9 @@ void clodb200_shutdown(void)
 	std::lock_guard<std::mutex> lock(g_api_mutex);
 	if (!g_initialized)
 		return;
-	g_ws.persist.destroy();
-	g_ws.temp.destroy();
-	g_ws.stage.destroy();
-#ifndef CLODB_EMU
-	if (t_context_ready)
-		cudaStreamDestroy(g_stream);
-	g_stream = 0;
-#endif
-	t_context_ready = false; // contexts of other threads are left to process exit
+	release_thread_context();
+	// the contexts of other threads are released by those threads: at their next call (stale generation) or when they exit
+	g_generation.fetch_add(1);
 	g_initialized = false;
 }
 
@@ -566,7 +609,14 @@ struct DeviceBlock
 	void* ptr;
 	size_t bytes;
 };
-static thread_local std::vector<DeviceBlock> g_block_cache;
+static thread_local std::vector<DeviceBlock>* t_block_cache = nullptr;
+static std::vector<DeviceBlock>& block_cache_ref()
+{
+	if (!t_block_cache)
+		t_block_cache = new std::vector<DeviceBlock>();
+	return *t_block_cache;
+}
+#define g_block_cache (block_cache_ref())
 
 static void* block_alloc(size_t bytes, std::vector<DeviceBlock>& owned)
 {
@@ -742,7 +792,11 @@ static size_t build_locked(const clodb200_config& config, const clodb200_device_
 	if (const char* e = getenv("CLODB200_TEMP_BYTES_BASE")) // tests start from a starved slab to exercise the growth path
 		base_temp = size_t(atoll(e));
 	ensure_workspace(T * scale_persist + V * 32 + (64u << 20), T * scale_temp + V * 16 + base_temp);
-	return build_dag(to_config(&config), dm->mesh, dm->indices, dm->index_count, g_ws, sink, g_last_build_stats);
+	size_t clusters = build_dag(to_config(&config), dm->mesh, dm->indices, dm->index_count, g_ws, sink, g_last_build_stats);
+	// optional instrumentation counter of the reference (clusterlod.h:33-35, incremented at :474-475)
+	if (config.partition_refined_split_count)
+		*config.partition_refined_split_count += g_last_build_stats.refined_splits;
+	return clusters;
 }
 
 size_t clodb200_meshBuildEx(clodb200_config config, const clodb200_device_mesh* mesh, void* output_context, clodb200_outputEx output_callback)
@@ -1284,6 +1338,68 @@ int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char*
 #ifndef CLODB_EMU
 static thread_local cudaEvent_t g_timer_start = nullptr, g_timer_stop = nullptr;
 #endif
+
+extern "C++"
+{
+namespace
+{
+void release_thread_context() noexcept
+{
+	if (!t_context_ready)
+		return;
+	try
+	{
+#ifndef CLODB_EMU
+		if (g_stream)
+			cudaStreamSynchronize(g_stream);
+#endif
+		dev_d2h_async_wait();
+	}
+	catch (...)
+	{
+	}
+	try
+	{
+		if (t_ws)
+		{
+			t_ws->persist.destroy();
+			t_ws->temp.destroy();
+			t_ws->stage.destroy();
+			delete t_ws;
+			t_ws = nullptr;
+		}
+		if (t_block_cache)
+		{
+			for (const DeviceBlock& b : *t_block_cache)
+				dev_free(b.ptr);
+			delete t_block_cache;
+			t_block_cache = nullptr;
+		}
+		delete g_record_pool;
+		g_record_pool = nullptr;
+		if (g_artifacts_pool)
+		{
+			g_artifacts_pool->data.pages.destroy();
+			delete g_artifacts_pool;
+			g_artifacts_pool = nullptr;
+		}
+#ifndef CLODB_EMU
+		if (g_timer_start)
+		{
+			cudaEventDestroy(g_timer_start);
+			cudaEventDestroy(g_timer_stop);
+			g_timer_start = g_timer_stop = nullptr;
+		}
+#endif
+	}
+	catch (...)
+	{
+	}
+	rt_thread_release();
+	t_context_ready = false;
+}
+} // namespace
+} // extern "C++"
 
 void clodb200_timerStart(void)
 {

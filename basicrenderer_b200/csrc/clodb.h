@@ -94,6 +94,7 @@ struct GroupSet
 	u32* group_cluster_offset = nullptr; // group_count + 1
 	std::vector<u32> group_cluster_offset_host;
 	u32 merge_rounds = 0;
+	u32 refined_splits = 0; // partitions the refined-id cap had to split (clusterlod.h:474-475)
 };
 // clod::partition (clusterlod.h:350-510) for the pending clusters of one level (all K clusters of the ClusterSet)
 GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 cluster_count, const int* cluster_refined, const float* cluster_bounds5, const u32* remap, const float* positions, size_t vertex_count, const Config& config, Workspace& ws);

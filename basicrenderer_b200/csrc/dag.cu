@@ -210,6 +210,7 @@ size_t build_dag(const Config& config, const DeviceMesh& mesh, const u32* indice
 		GroupSet groups = partition_clusters(level.tri, level.cluster_tri_offset, K, refined_dev, bounds5, remap, mesh.positions, V, config, ws);
 		u32 G = groups.group_count;
 		stats.level_groups.push_back(G);
+		stats.refined_splits += groups.refined_splits;
 		double t_partition = clock.lap();
 		u64 launches0 = g_launches;
 

@@ -53,6 +53,7 @@ struct BuildStats
 	u32 simplify_passes = 0;
 	u32 simplify_rounds = 0;
 	std::vector<u32> level_triangles, level_clusters, level_groups;
+	size_t refined_splits = 0; // partitions split by the refined-id cap (clodConfig::partition_refined_split_count)
 	std::vector<u32> level_passes, level_sloppy; // edge-collapse passes / groups sent through the sloppy fallback, per level
 };
 

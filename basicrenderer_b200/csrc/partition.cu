@@ -919,7 +919,7 @@ DEVFN void refined_cap_split(u32 begin, u32 n, u32* group_clusters, const int* _
 		buckets_in_current++;
 	}
 	if (extra)
-		atomicAdd(extra_groups, extra);
+		atomicAdd(extra_groups, 1u); // one per split partition, as the reference's instrumentation counter counts
 }
 
 KERNEL k_refined_cap(const u32* __restrict__ group_offset, u32* group_clusters, const int* __restrict__ cluster_refined, u32 G, u32 cap, u32* scratch_clusters, u32* split_marks, u32* extra_groups)
@@ -1257,6 +1257,7 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 	LAUNCH(k_emit_group_offsets, size_t(K) + 1, marks, marks_scanned, K, G_final, out.group_cluster_offset);
 
 	out.group_count = G_final;
+	out.refined_splits = cap > 0 && G_final != G ? dev_read(scalars + 2) : 0;
 	out.group_cluster_offset_host = dev_download(out.group_cluster_offset, size_t(G_final) + 1);
 	out.merge_rounds = 0;
 	return out;

@@ -214,8 +214,24 @@ struct ProfileSpan
 	cudaEvent_t start, stop;
 	size_t threads;
 };
-thread_local std::vector<ProfileSpan> g_spans;
-thread_local std::vector<cudaEvent_t> g_event_pool;
+// Heap objects behind trivially destructible thread_local pointers: rt_thread_release() may run from another thread_local's
+// destructor at thread exit, when thread_local objects with destructors of their own could already be gone.
+thread_local std::vector<ProfileSpan>* t_spans = nullptr;
+thread_local std::vector<cudaEvent_t>* t_event_pool = nullptr;
+std::vector<ProfileSpan>& spans_ref()
+{
+	if (!t_spans)
+		t_spans = new std::vector<ProfileSpan>();
+	return *t_spans;
+}
+std::vector<cudaEvent_t>& event_pool_ref()
+{
+	if (!t_event_pool)
+		t_event_pool = new std::vector<cudaEvent_t>();
+	return *t_event_pool;
+}
+#define g_spans (spans_ref())
+#define g_event_pool (event_pool_ref())
 
 cudaEvent_t take_event()
 {
@@ -316,6 +332,53 @@ void scan_chain_reserve(size_t tiles)
 	g_scan_chain.capacity_tiles = cap;
 }
 #endif
+
+void rt_thread_release() noexcept
+{
+#ifndef CLODB_EMU
+	// errors are ignored on purpose: at process exit the CUDA runtime may already be unloading
+	if (g_stream)
+		cudaStreamSynchronize(g_stream);
+	if (g_copy_stream)
+	{
+		cudaStreamSynchronize(g_copy_stream);
+		cudaStreamDestroy(g_copy_stream);
+		cudaEventDestroy(g_copy_ready);
+		cudaEventDestroy(g_copy_done);
+		g_copy_stream = nullptr;
+		g_copy_ready = g_copy_done = nullptr;
+	}
+	if (g_pinned_ring)
+		cudaFreeHost(g_pinned_ring);
+	g_pinned_ring = nullptr;
+	g_ring_next = 0;
+	cudaFree(g_scan_chain.desc);
+	cudaFree(g_scan_chain.desc64);
+	cudaFree(g_scan_chain.box_desc);
+	g_scan_chain = ScanChain();
+	if (t_spans)
+	{
+		for (const ProfileSpan& s : *t_spans)
+		{
+			cudaEventDestroy(s.start);
+			cudaEventDestroy(s.stop);
+		}
+		delete t_spans;
+		t_spans = nullptr;
+	}
+	if (t_event_pool)
+	{
+		for (cudaEvent_t e : *t_event_pool)
+			cudaEventDestroy(e);
+		delete t_event_pool;
+		t_event_pool = nullptr;
+	}
+	if (g_stream)
+		cudaStreamDestroy(g_stream);
+	g_stream = 0;
+	cudaGetLastError();
+#endif
+}
 
 void Arena::init(size_t bytes)
 {

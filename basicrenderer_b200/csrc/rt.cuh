@@ -225,6 +225,10 @@ void profile_set_last_work(size_t items);
 // drains recorded events; returns "name,launches,total_ms,total_threads\n" lines sorted by time
 std::string profile_report();
 
+// Frees everything the runtime layer holds for the calling thread (build stream, copy stream and events, pinned upload ring,
+// scan-chain descriptors, profiling events). Never throws: it runs from thread-exit destructors and from shutdown.
+void rt_thread_release() noexcept;
+
 // ---- raw device memory -------------------------------------------------------------------------------------------
 void* dev_malloc(size_t bytes);
 void dev_free(void* p);

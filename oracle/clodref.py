@@ -101,7 +101,7 @@ _BLOB_DTYPES = {
     "out.cluster_refined": np.int32, "out.cluster_bounds": np.float32, "out.cluster_vertex_count": np.uint32,
     "out.cluster_indices": np.uint32, "out.cluster_index_offsets": np.uint32,
     "stats.level_groups": np.uint32, "stats.level_clusters": np.uint32, "stats.level_triangles": np.uint32, "stats.level_sloppy": np.uint32,
-    "stats.level_max_error": np.float32,
+    "stats.level_max_error": np.float32, "stats.group_error": np.float32, "stats.group_depth": np.int32, "stats.group_clusters": np.uint32,
 }
 
 
@@ -200,7 +200,7 @@ def dag_build_stats(positions, indices, attributes=None, attribute_weights=None,
     threads = threads or os.cpu_count() or 1
     h = lib().clodref_dag_build_stats(C.byref(cfg), _ptr(indices), indices.size, _ptr(positions), positions.shape[0], 12, _ptr(attributes), astride, _ptr(attribute_weights), acount, protect_mask, threads)
     d = Dag(h)
-    out = {k.split(".", 1)[1]: d.get(k) for k in ("stats.level_groups", "stats.level_clusters", "stats.level_triangles", "stats.level_sloppy", "stats.level_max_error")}
+    out = {k.split(".", 1)[1]: d.get(k) for k in ("stats.level_groups", "stats.level_clusters", "stats.level_triangles", "stats.level_sloppy", "stats.level_max_error", "stats.group_error", "stats.group_depth", "stats.group_clusters")}
     out["total_clusters"] = d.cluster_count
     d.close()
     return out

@@ -264,10 +264,14 @@ size_t clodref_dag_build_mt(const clodConfig* config, const unsigned int* indice
 // (no index lists): what the scale-parity tests compare at sizes where a full dump would take minutes.
 //   stats.level_groups / level_clusters / level_triangles (u32 per depth), stats.level_max_error (f32, finite errors only),
 //   stats.level_sloppy (u32: fallback calls while that depth's groups were simplified)
+//   stats.group_error (f32) / group_depth (i32) / group_clusters (u32): one entry per emitted group, callback order
 struct StatsRecorder
 {
 	std::vector<uint32_t> groups, clusters, triangles, sloppy;
 	std::vector<float> max_error;
+	std::vector<float> group_error; // every group's emitted error, callback order
+	std::vector<int32_t> group_depth;
+	std::vector<uint32_t> group_clusters;
 	int next_group = 0;
 	unsigned int sloppy_seen = 0;
 
@@ -293,6 +297,9 @@ struct StatsRecorder
 		r->sloppy[d] += now - r->sloppy_seen;
 		r->sloppy_seen = now;
 		r->groups[d]++;
+		r->group_error.push_back(group.simplified.error);
+		r->group_depth.push_back(group.depth);
+		r->group_clusters.push_back(uint32_t(cluster_count));
 		r->clusters[d] += uint32_t(cluster_count);
 		for (size_t i = 0; i < cluster_count; ++i)
 			r->triangles[d] += uint32_t(cl[i].index_count / 3);
@@ -318,6 +325,9 @@ clodref_handle* clodref_dag_build_stats(const clodConfig* config, const unsigned
 	h->store.put("stats.level_triangles", rec.triangles);
 	h->store.put("stats.level_sloppy", rec.sloppy);
 	h->store.put("stats.level_max_error", rec.max_error);
+	h->store.put("stats.group_error", rec.group_error);
+	h->store.put("stats.group_depth", rec.group_depth);
+	h->store.put("stats.group_clusters", rec.group_clusters);
 	return h;
 }
 

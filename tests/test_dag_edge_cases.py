@@ -1,20 +1,12 @@
 """Whole-DAG parity on awkward inputs, against the compiled reference (clodBuildEx of clusterlod.h + meshoptimizer): degenerate
 and zero-area triangles, unwelded triangle soup, disconnected components, non-manifold edges, tiny meshes, fully locked
 meshes, position-only meshes. The meshes are small enough that every level is one group, so the callback stream must equal
-the reference's bit for bit. Runs on the host emulation of the kernel sources (stage logic; the CUDA library runs the same
-sources and is compared with the reference on the regular meshes by test_dag.py / test_stages.py with -m gpu)."""
+the reference's bit for bit. Every case runs twice (conftest `lib`): on the host emulation of the kernel sources (no GPU) and,
+with -m gpu, on the product CUDA library through the C ABI - the warp-cooperative kernel bodies only exist there."""
 import numpy as np
 import pytest
 
 from basicrenderer_b200 import invariants, meshgen
-
-
-@pytest.fixture(scope="module")
-def emu():
-    from basicrenderer_b200 import build
-    from basicrenderer_b200.api import ClodLib
-
-    return ClodLib(build.build_emu())
 
 
 def _soup(m):
@@ -70,14 +62,14 @@ CASES = _cases()
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_edge_case_dag_equals_reference(emu, oracle, name):
+def test_edge_case_dag_equals_reference(lib, oracle, name):
     positions, normals, indices, vertex_lock = CASES[name]
     positions = np.ascontiguousarray(positions, np.float32)
     indices = np.ascontiguousarray(indices, np.uint32)
     kw = dict(attributes=normals, attribute_weights=np.ones(3, np.float32), protect_mask=7) if normals is not None else {}
     if vertex_lock is not None:
         kw["vertex_lock"] = vertex_lock
-    rec = emu.build_dag(positions, indices, **kw)
+    rec = lib.build_dag(positions, indices, **kw)
     invariants.check_dag(rec, positions, indices, remap=oracle.position_remap(positions))
     if vertex_lock is not None:
         # the oracle's dump driver has no vertex_lock input: with every vertex locked nothing can collapse, so every group
@@ -96,7 +88,7 @@ def test_edge_case_dag_equals_reference(emu, oracle, name):
 
 
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n][1] is not None and CASES[n][3] is None])
-def test_edge_case_artifacts_equal_the_unmodified_reference_builder(emu, name):
+def test_edge_case_artifacts_equal_the_unmodified_reference_builder(lib, name):
     """The whole outer call (BuildClusterLODArtifactsFromGeometry with the reference's OWN clodBuildEx) against ours: every
     table and every page byte, on inputs where the grouping is forced."""
     from oracle import clodfull
@@ -110,13 +102,13 @@ def test_edge_case_artifacts_equal_the_unmodified_reference_builder(emu, name):
     v = art.interleave(np.ascontiguousarray(positions, np.float32), normals)
     indices = np.ascontiguousarray(indices, np.uint32)
     ref = clodfull.build(v, indices)
-    ours = emu.build_artifacts(v, indices, art.VERTEX_NORMALS)
+    ours = lib.build_artifacts(v, indices, art.VERTEX_NORMALS)
     if np.bincount(np.asarray(ref.groups["depth"])).max() > 1:
         pytest.skip("reference uses several groups on some level")
     _assert_identical(ref, ours)
 
 
-def test_dense_adjacency_soup_grows_the_slab_and_keeps_the_invariants(emu, oracle):
+def test_dense_adjacency_soup_grows_the_slab_and_keeps_the_invariants(lib, oracle):
     """20 000 random triangles over 1 000 points: every vertex is shared by ~60 triangles spread over dozens of meshlets, so the
     cluster adjacency (pairs of clusters sharing a vertex) is two orders of magnitude denser than a surface's and does not fit
     the slab sized from the triangle count; the build grows it and starts again (capi.cu with_arena_growth). The reference
@@ -126,6 +118,6 @@ def test_dense_adjacency_soup_grows_the_slab_and_keeps_the_invariants(emu, oracl
     nrm = rng.standard_normal((1000, 3)).astype(np.float32)
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     tri = rng.integers(0, 1000, (20000, 3)).astype(np.uint32).reshape(-1)
-    rec = emu.build_dag(pts, tri, attributes=nrm, attribute_weights=np.ones(3, np.float32), protect_mask=7)
+    rec = lib.build_dag(pts, tri, attributes=nrm, attribute_weights=np.ones(3, np.float32), protect_mask=7)
     stats = invariants.check_dag(rec, pts, tri, remap=oracle.position_remap(pts))
     assert stats[0]["triangles"] == 20000 and rec.total_clusters >= 20000 // 128

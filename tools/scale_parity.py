@@ -39,7 +39,7 @@ def mesh_attributes(m):
     return m.normals, np.ones(3, np.float32)
 
 
-def ours_stats(lib, m):
+def ours_stats(lib, m, keep_groups=False):
     attrs, w = mesh_attributes(m)
     t0 = time.time()
     h = lib.upload_mesh(m.positions, m.indices, attributes=attrs, attribute_weights=w, protect_mask=7)
@@ -55,7 +55,9 @@ def ours_stats(lib, m):
     for d in range(levels):
         e = err[(depth == d) & (err < FLT_MAX)]
         max_err[d] = e.max() if e.size else 0.0
+    extra = {"group_error": np.asarray(err).copy(), "group_depth": np.asarray(depth).copy()} if keep_groups else {}
     return {
+        **extra,
         "level_triangles": rec.level_triangles.astype(np.int64), "level_groups": rec.level_groups.astype(np.int64),
         "level_sloppy": rec.level_sloppy.astype(np.int64), "level_passes": rec.level_passes.astype(np.int64),
         "level_max_error": max_err, "groups": rec.groups, "meshlets": rec.total_clusters, "seconds": dt,
