@@ -643,7 +643,8 @@ static __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_rounds(MergeA
 		for (u32 base = gtid - (gtid & 31); base <= mask; base += gsize)
 		{
 			u32 slot = base + (gtid & 31);
-			u64 key = a.table_key[slot];
+			// tables of fewer than 32 slots (a handful of edges on a small level) end inside the warp's first chunk
+			u64 key = slot <= mask ? a.table_key[slot] : EDGE_EMPTY;
 			bool take = key != EDGE_EMPTY;
 			u32 pos = warp_append(take, a.state + 1);
 			if (take)

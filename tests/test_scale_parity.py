@@ -6,8 +6,8 @@ groups per level, the large-scan code paths) and C2 itself (10 M, the benched me
 
   I6   triangles within +-2 % of the reference's (north_star bar; observed: <= 0.05 %)
   -    the number of groups that needed the sloppy fallback equals the reference's (0 on these meshes)
-  I7   simplification error: median and 90th percentile of the group errors within 5 % of the reference's on levels with
-       enough groups for the statistic to mean something; the per-level MAX is reported and bounded by the reference's own
+  I7   simplification error: median and 90th percentile of the depth-0 group errors (the only raw simplification errors the
+       output carries) within 5 % of the reference's; the per-level MAX is reported and bounded by the reference's own
        sensitivity to its input order (tools/noise_floor.py: the unmodified reference against itself on the same surface with the
        triangle order reversed or x/y mirrored moves the per-level max by 1.2x - 1.9x), because the grouping stage is an
        invariant-bar stage (north_star) and every level above the first inherits the grouping of the levels below
@@ -46,14 +46,13 @@ def _check(lib, oracle, spec, expect_golden):
         assert r["groups"] <= 2 * r["ref_groups"] + 1, r
         if r["ref_max_error"] > 0:
             assert r["error_ratio"] <= MAX_ERROR_NOISE_BAR, r
-    # I7 on distribution statistics of the group errors
-    for d in range(summary["levels"]):
-        a = ours["group_error"][(ours["group_depth"] == d) & (ours["group_error"] < sp.FLT_MAX)]
-        b = ref["group_error"][(ref["group_depth"] == d) & (ref["group_error"] < sp.FLT_MAX)]
-        if min(a.size, b.size) < QUANTILE_MIN_GROUPS:
-            continue
+    # I7 on distribution statistics of the raw simplification errors. Only depth 0 emits them: above it a group's error is
+    # max(1.5 x inherited, own) (clusterlod.h:733), i.e. mostly the inherited maximum of the levels below.
+    a = ours["group_error"][(ours["group_depth"] == 0) & (ours["group_error"] < sp.FLT_MAX)]
+    b = ref["group_error"][(ref["group_depth"] == 0) & (ref["group_error"] < sp.FLT_MAX)]
+    if min(a.size, b.size) >= QUANTILE_MIN_GROUPS:
         for q in (50, 90):
-            assert np.percentile(a, q) <= QUANTILE_BAR * np.percentile(b, q), (spec, d, q, np.percentile(a, q), np.percentile(b, q))
+            assert np.percentile(a, q) <= QUANTILE_BAR * np.percentile(b, q), (spec, q, np.percentile(a, q), np.percentile(b, q))
     # terminal flags (FLT_MAX) exactly where simplified > 0.85 x input: same count per level as the reference
     for d in range(summary["levels"]):
         assert np.sum((ours["group_depth"] == d) & (ours["group_error"] >= sp.FLT_MAX)) == np.sum((ref["group_depth"] == d) & (ref["group_error"] >= sp.FLT_MAX)), (spec, d)
