@@ -1092,110 +1092,286 @@ KERNEL k_wave_decide(const u32* __restrict__ list, u32 n, const u32* __restrict_
 	wave_decide_item(list[i], sorted_cand, status, cand_v0, cand_v1, remap, wedge, kind, loop, loopback, vpos, idx, adj_off, adj_corner, vmin_any, vmin_src, round_tag, collapse_remap, collapse_locked);
 }
 #else
-// Same step as wave_decide_item, executed by 8 cooperating lanes (gmask) per candidate: the two walks over the adjacency of
-// r0 are split across the lanes, which shortens the dependent-load chain of a round from ~50 to ~10 memory latencies. All 8
-// lanes pass the same k and receive the same result.
-DEVFN bool wave_decide_coop8(u32 k, bool valid, unsigned gmask, u32 lane8, const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap,
-    const u32* __restrict__ wedge, const u8* __restrict__ kind, const u32* __restrict__ loop, const u32* __restrict__ loopback, const Vector3* __restrict__ vpos, const u32* __restrict__ idx, const u32* __restrict__ adj_off,
-    const u32* __restrict__ adj_corner, const u64* __restrict__ vmin_any, const u64* __restrict__ vmin_src, u32 round_tag, u32* collapse_remap, u8* collapse_locked)
+// ---- persistent wavefront kernel ------------------------------------------------------------------------------------------
+// All wavefront rounds of a pass in one cooperative launch. What a round costs is a chain of dependent gathers per undecided
+// candidate and the barrier between rounds, so the kernel is organised around both:
+//   * the work list holds 16-byte records {sorted position, r0, r1, candidate}: the position classes of both endpoints are
+//     resolved once, when the candidate is listed, and a round starts with one coalesced record load followed by four
+//     INDEPENDENT gathers (two lock bytes, two vertex minima);
+//   * a candidate that stays undecided publishes itself for the NEXT round while it is appended to the next list (vertex
+//     minima are double buffered by round parity), so a round needs one grid barrier instead of two;
+//   * only candidates that are minimal at both endpoints walk the adjacency of r0; they are compacted inside the warp and
+//     handled by 8 cooperating lanes each (the two walks have ~6-12 entries);
+//   * once the list is short (tail_threshold) the other CTAs leave and CTA 0 finishes the remaining rounds alone, separated by
+//     __syncthreads() instead of grid barriers: the tail is a long sequence of almost empty rounds (dependency chains).
+// Mutable arrays are read with ld.global.cg: in the single-CTA tail the values were written by other warps of the same SM
+// between two __syncthreads(), and L1 must not serve an older copy.
+struct WaveEntry
 {
-	if (!valid)
-		return false;
-	u32 c = sorted_cand[k];
-	u32 i0 = cand_v0[c], i1 = cand_v1[c];
-	u32 r0 = remap[i0], r1 = remap[i1];
-	if (collapse_locked[r0] | collapse_locked[r1])
-	{
-		if (lane8 == 0)
-			status[k] = Status_Locked;
-		return false;
-	}
-	if (wave_min(vmin_any, r0, round_tag) != k || wave_min(vmin_any, r1, round_tag) != k)
-		return true;
-	u32 begin = adj_off[r0], end = adj_off[r0 + 1];
-	bool wait = false;
-	for (u32 e = begin + lane8; e < end; e += 8)
-	{
-		u32 corner = adj_corner[e];
-		u32 a = remap[idx[corner_next(corner)]], b = remap[idx[corner_prev(corner)]];
-		wait |= wave_min(vmin_src, a, round_tag) < k || wave_min(vmin_src, b, round_tag) < k;
-	}
-	if (__ballot_sync(gmask, wait))
-		return true;
-	bool flip = false;
-	{
-		const Vector3 v0 = vpos[r0];
-		const Vector3 v1 = vpos[r1];
-		for (u32 e = begin + lane8; e < end; e += 8)
-		{
-			u32 corner = adj_corner[e];
-			u32 a = collapse_remap[remap[idx[corner_next(corner)]]];
-			u32 b = collapse_remap[remap[idx[corner_prev(corner)]]];
-			if (a == r1 || b == r1 || a == b)
-				continue;
-			flip |= has_triangle_flip(vpos[a], vpos[b], v0, v1);
-		}
-	}
-	if (__ballot_sync(gmask, flip))
-	{
-		if (lane8 == 0)
-			status[k] = Status_Flip;
-		return false;
-	}
-	if (lane8 == 0)
-	{
-		u8 kd = kind[i0];
-		if (kd == Kind_Complex)
-		{
-			u32 v = i0;
-			do
-			{
-				collapse_remap[v] = get_complex_target(v, i1, remap, loop, loopback);
-				v = wedge[v];
-			} while (v != i0);
-		}
-		else if (kd == Kind_Seam)
-		{
-			u32 s0 = wedge[i0];
-			u32 s1 = loop[i0] == i1 ? loopback[s0] : loop[s0];
-			s1 = (s1 != NONE) ? s1 : wedge[i1];
-			collapse_remap[i0] = i1;
-			collapse_remap[s0] = s1;
-		}
-		else
-		{
-			collapse_remap[i0] = i1;
-		}
-		collapse_locked[r0] = 1;
-		collapse_locked[r1] = 1;
-		status[k] = Status_Performed;
-	}
-	return false;
-}
+	u32 k, r0, r1, c;
+};
 
-// Persistent cooperative kernel: all wavefront rounds of a pass in one launch. The undecided candidates are kept as a
-// compacted work list (double buffered, warp-aggregated appends), so a round only touches what is still undecided;
-// rounds are separated by grid-wide barriers instead of kernel launches.
-//   list[0] / state[0] hold the initial work list and its length; state[1] must be zero on entry;
-//   state[0..1] list counters, state[2] running round tag, state[3] rounds executed, state[4] undecided left,
-//   state[5] total rounds of all passes, state[6] max rounds in a pass, state[8..9] (u64) work items (candidate x round) of this launch
+// state[0..2] list counters (round r appends through state[r % 3]); [3] running round tag; [4] rounds of this launch;
+// [5] undecided left; [6] rounds of all launches; [7] max rounds in a launch; [8..9] (u64) work items (candidate x round)
 struct WaveArgs
 {
-	const u32* sorted_cand;
 	u8* status;
 	const u32 *cand_v0, *cand_v1, *remap, *wedge;
 	const u8* kind;
 	const u32 *loop, *loopback;
 	const Vector3* vpos;
 	const u32 *idx, *adj_off, *adj_corner;
-	u64 *vmin_any, *vmin_src;
+	u64* vmin_any[2];
+	u64* vmin_src[2];
 	u32* collapse_remap;
 	u8* collapse_locked;
-	u32* list[2];
+	WaveEntry* list[2];
 	u32* state;
-	u32 cand_total, max_rounds;
+	u32 max_rounds, tail_threshold;
 	u32* round_log; // optional (debug): per round {active count, globaltimer ns low word at round end}
 };
+
+DEVFN u32 wave_min_cg(const u64* vmin, u32 v, u32 round_tag)
+{
+	u64 x = __ldcg(reinterpret_cast<const unsigned long long*>(vmin + v));
+	return u32(x >> 32) == ~round_tag ? u32(x) : NONE;
+}
+
+DEVFN void wave_publish_entry(const WaveEntry& e, u64* vmin_any, u64* vmin_src, u32 round_tag)
+{
+	unsigned long long value = (u64(~round_tag) << 32) | u64(e.k);
+	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_any[e.r0]), value);
+	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_any[e.r1]), value);
+	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_src[e.r0]), value);
+}
+
+// lists the undecided candidates of the current windows as records and publishes them for the first round
+static __global__ void __launch_bounds__(256) k_wave_list(const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_group, const GroupState* __restrict__ groups, const u8* __restrict__ status,
+    const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, WaveArgs a, u32 cand_total)
+{
+	size_t kk = GTID;
+	bool take = false;
+	WaveEntry e = {0, 0, 0, 0};
+	if (kk < cand_total && status[kk] == Status_Undecided)
+	{
+		u32 c = sorted_cand[kk];
+		const GroupState& gs = groups[cand_group[c]];
+		take = u32(kk) >= gs.win_begin && u32(kk) < gs.win_end;
+		if (take)
+		{
+			e.k = u32(kk);
+			e.c = c;
+			e.r0 = remap[cand_v0[c]];
+			e.r1 = remap[cand_v1[c]];
+		}
+	}
+	unsigned mask = __ballot_sync(0xffffffffu, take);
+	if (mask)
+	{
+		u32 lane = threadIdx.x & 31;
+		u32 off = 0;
+		if (lane == u32(__ffs(mask) - 1))
+			off = atomicAdd(a.state, u32(__popc(mask)));
+		off = __shfl_sync(0xffffffffu, off, __ffs(mask) - 1);
+		if (take)
+		{
+			a.list[0][off + __popc(mask & ((1u << lane) - 1))] = e;
+			u32 tag = a.state[3] + 1;
+			wave_publish_entry(e, a.vmin_any[tag & 1], a.vmin_src[tag & 1], tag);
+		}
+	}
+}
+
+// The part of the decide step that walks the adjacency of r0, executed by the 8 lanes of gmask for a candidate that is minimal
+// at both endpoints. Returns 1 while the candidate has to wait for a lower-ranked collapse next to it, else 0 (decided).
+DEVFN int wave_walk8(const WaveArgs& a, u32 k, u32 r0, u32 r1, u32 c, unsigned gmask, u32 lane8, const u64* __restrict__ src_cur, u32 tag)
+{
+	const u32 begin = a.adj_off[r0], end = a.adj_off[r0 + 1];
+	bool wait = false;
+	for (u32 e = begin + lane8; e < end; e += 8)
+	{
+		u32 corner = a.adj_corner[e];
+		u32 va = a.remap[a.idx[corner_next(corner)]], vb = a.remap[a.idx[corner_prev(corner)]];
+		wait |= wave_min_cg(src_cur, va, tag) < k || wave_min_cg(src_cur, vb, tag) < k;
+	}
+	if (__ballot_sync(gmask, wait))
+		return 1;
+	bool flip = false;
+	{
+		const Vector3 v0 = a.vpos[r0];
+		const Vector3 v1 = a.vpos[r1];
+		for (u32 e = begin + lane8; e < end; e += 8)
+		{
+			u32 corner = a.adj_corner[e];
+			u32 va = __ldcg(&a.collapse_remap[a.remap[a.idx[corner_next(corner)]]]);
+			u32 vb = __ldcg(&a.collapse_remap[a.remap[a.idx[corner_prev(corner)]]]);
+			if (va == r1 || vb == r1 || va == vb)
+				continue;
+			flip |= has_triangle_flip(a.vpos[va], a.vpos[vb], v0, v1);
+		}
+	}
+	if (__ballot_sync(gmask, flip))
+	{
+		if (lane8 == 0)
+			a.status[k] = Status_Flip;
+		return 0;
+	}
+	if (lane8 == 0)
+	{
+		u32 i0 = a.cand_v0[c], i1 = a.cand_v1[c];
+		u8 kd = a.kind[i0];
+		if (kd == Kind_Complex)
+		{
+			u32 v = i0;
+			do
+			{
+				a.collapse_remap[v] = get_complex_target(v, i1, a.remap, a.loop, a.loopback);
+				v = a.wedge[v];
+			} while (v != i0);
+		}
+		else if (kd == Kind_Seam)
+		{
+			u32 s0 = a.wedge[i0];
+			u32 s1 = a.loop[i0] == i1 ? a.loopback[s0] : a.loop[s0];
+			s1 = (s1 != NONE) ? s1 : a.wedge[i1];
+			a.collapse_remap[i0] = i1;
+			a.collapse_remap[s0] = s1;
+		}
+		else
+		{
+			a.collapse_remap[i0] = i1;
+		}
+		a.collapse_locked[r0] = 1;
+		a.collapse_locked[r1] = 1;
+		a.status[k] = Status_Performed;
+	}
+	return 0;
+}
+
+// one round over cur[0..n): decide, and append + publish (for round tag + 1) what stays undecided. Executed by `nthreads`
+// threads (the whole grid, or one CTA in the tail); tid is the thread's rank among them.
+DEVFN void wave_round(const WaveArgs& a, const WaveEntry* cur, u32 n, WaveEntry* next, u32* counter, u32 tag, u32 tid, u32 nthreads)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 sub = lane >> 3, lane8 = lane & 7;
+	const unsigned gmask = 0xffu << (sub * 8);
+	const u64* any_cur = a.vmin_any[tag & 1];
+	const u64* src_cur = a.vmin_src[tag & 1];
+	u64* any_nxt = a.vmin_any[(tag + 1) & 1];
+	u64* src_nxt = a.vmin_src[(tag + 1) & 1];
+	for (u32 base = tid - lane; base < n; base += nthreads)
+	{
+		const u32 i = base + lane;
+		const bool valid = i < n;
+		WaveEntry e = {0, 0, 0, 0};
+		bool undecided = false, ready = false;
+		if (valid)
+		{
+			uint4 raw = __ldcg(reinterpret_cast<const uint4*>(cur + i));
+			e.k = raw.x, e.r0 = raw.y, e.r1 = raw.z, e.c = raw.w;
+			// four independent gathers. A lock set by any decided collapse is final: locks are only ever set by lower-ranked
+			// candidates (see the file header)
+			u32 l0 = __ldcg(&a.collapse_locked[e.r0]), l1 = __ldcg(&a.collapse_locked[e.r1]);
+			u32 m0 = wave_min_cg(any_cur, e.r0, tag), m1 = wave_min_cg(any_cur, e.r1, tag);
+			if (l0 | l1)
+				a.status[e.k] = Status_Locked;
+			else if (m0 != e.k || m1 != e.k)
+				undecided = true;
+			else
+				ready = true;
+		}
+		unsigned rmask = __ballot_sync(0xffffffffu, ready);
+		while (rmask)
+		{
+			// the sub-th ready lane of this batch of (up to) four is handled by the 8 lanes of group `sub`
+			const u32 src = __fns(rmask, 0, sub + 1);
+			const bool active = src != 0xffffffffu;
+			const u32 from = active ? src : 0;
+			u32 k = __shfl_sync(0xffffffffu, e.k, from), r0 = __shfl_sync(0xffffffffu, e.r0, from), r1 = __shfl_sync(0xffffffffu, e.r1, from), c = __shfl_sync(0xffffffffu, e.c, from);
+			int res = 0;
+			if (active)
+				res = wave_walk8(a, k, r0, r1, c, gmask, lane8, src_cur, tag);
+			__syncwarp();
+			for (u32 s = 0; s < 4; ++s)
+			{
+				u32 owner = __fns(rmask, 0, s + 1);
+				int r = __shfl_sync(0xffffffffu, res, s * 8);
+				if (owner == lane)
+					undecided = r != 0;
+			}
+			// drop the (up to) four handled bits
+			for (int s = 0; s < 4 && rmask; ++s)
+				rmask &= rmask - 1;
+		}
+		unsigned umask = __ballot_sync(0xffffffffu, undecided);
+		if (umask)
+		{
+			int leader = __ffs(umask) - 1;
+			u32 off = 0;
+			if (int(lane) == leader)
+				off = atomicAdd(counter, u32(__popc(umask)));
+			off = __shfl_sync(0xffffffffu, off, leader);
+			if (undecided)
+			{
+				__stcg(reinterpret_cast<uint4*>(next + off + __popc(umask & ((1u << lane) - 1))), make_uint4(e.k, e.r0, e.r1, e.c));
+				wave_publish_entry(e, any_nxt, src_nxt, tag + 1);
+			}
+		}
+	}
+}
+
+// The same round with one candidate per 8-lane group (all lanes of the group hold the same record): used when the list is short
+// compared with the grid, where a round costs one chain of dependent loads whatever its size. Nothing is serialised inside a
+// warp, and the adjacency walk starts right after the four gathers.
+DEVFN void wave_round_groups(const WaveArgs& a, const WaveEntry* cur, u32 n, WaveEntry* next, u32* counter, u32 tag, u32 tid, u32 nthreads)
+{
+	const u32 lane = threadIdx.x & 31;
+	const u32 sub = lane >> 3, lane8 = lane & 7;
+	const unsigned gmask = 0xffu << (sub * 8);
+	const u64* any_cur = a.vmin_any[tag & 1];
+	const u64* src_cur = a.vmin_src[tag & 1];
+	u64* any_nxt = a.vmin_any[(tag + 1) & 1];
+	u64* src_nxt = a.vmin_src[(tag + 1) & 1];
+	for (u32 base = (tid >> 5) * 4; base < n; base += (nthreads >> 5) * 4)
+	{
+		const u32 i = base + sub;
+		const bool valid = i < n;
+		WaveEntry e = {0, 0, 0, 0};
+		bool undecided = false;
+		if (valid)
+		{
+			uint4 raw = __ldcg(reinterpret_cast<const uint4*>(cur + i));
+			e.k = raw.x, e.r0 = raw.y, e.r1 = raw.z, e.c = raw.w;
+			u32 l0 = __ldcg(&a.collapse_locked[e.r0]), l1 = __ldcg(&a.collapse_locked[e.r1]);
+			u32 m0 = wave_min_cg(any_cur, e.r0, tag), m1 = wave_min_cg(any_cur, e.r1, tag);
+			if (l0 | l1)
+			{
+				if (lane8 == 0)
+					a.status[e.k] = Status_Locked;
+			}
+			else if (m0 != e.k || m1 != e.k)
+				undecided = true;
+			else
+				undecided = wave_walk8(a, e.k, e.r0, e.r1, e.c, gmask, lane8, src_cur, tag) != 0;
+		}
+		__syncwarp();
+		const bool keep = undecided && lane8 == 0;
+		unsigned umask = __ballot_sync(0xffffffffu, keep);
+		if (umask)
+		{
+			int leader = __ffs(umask) - 1;
+			u32 off = 0;
+			if (int(lane) == leader)
+				off = atomicAdd(counter, u32(__popc(umask)));
+			off = __shfl_sync(0xffffffffu, off, leader);
+			if (keep)
+			{
+				__stcg(reinterpret_cast<uint4*>(next + off + __popc(umask & ((1u << lane) - 1))), make_uint4(e.k, e.r0, e.r1, e.c));
+				wave_publish_entry(e, any_nxt, src_nxt, tag + 1);
+			}
+		}
+	}
+}
 
 static const int WAVE_THREADS = 1024; // one CTA per SM: the grid barrier costs one atomic per CTA
 static __global__ void __launch_bounds__(WAVE_THREADS, 1) k_wave_rounds(WaveArgs a)
@@ -1203,46 +1379,28 @@ static __global__ void __launch_bounds__(WAVE_THREADS, 1) k_wave_rounds(WaveArgs
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const u32 gsize = gridDim.x * blockDim.x;
 	const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
-	const u32 lane = threadIdx.x & 31;
-	u32 n = *reinterpret_cast<volatile u32*>(a.state);
-	u32 tag = a.state[2];
-	const u32* cur = a.list[0];
+	volatile u32* vstate = a.state;
+	u32 n = vstate[0];
+	u32 tag = vstate[3];
 	u32 round = 0;
 	unsigned long long items = 0;
-	while (n != 0)
+	bool tail = false;
+	while (n != 0 && round < a.max_rounds)
 	{
+		if (gridDim.x > 1 && n <= a.tail_threshold)
+		{
+			tail = true;
+			break;
+		}
 		++round;
 		++tag;
 		items += n;
-		for (u32 i = gtid; i < n; i += gsize)
-			wave_publish_item(cur[i], a.sorted_cand, a.cand_v0, a.cand_v1, a.remap, a.vmin_any, a.vmin_src, tag);
-		grid.sync();
-		u32* next = a.list[round & 1];
-		u32* counter = a.state + (round & 1);
 		if (gtid == 0)
-			a.state[(round + 1) & 1] = 0;
-		const u32 sub = lane >> 3, lane8 = lane & 7;
-		const unsigned gmask = 0xffu << (sub * 8);
-		for (u32 base = (gtid >> 5) * 4; base < n; base += (gsize >> 5) * 4)
-		{
-			u32 i = base + sub;
-			bool valid = i < n;
-			u32 k = valid ? cur[i] : 0;
-			bool undecided = wave_decide_coop8(k, valid, gmask, lane8, a.sorted_cand, a.status, a.cand_v0, a.cand_v1, a.remap, a.wedge, a.kind, a.loop, a.loopback, a.vpos, a.idx, a.adj_off, a.adj_corner, a.vmin_any, a.vmin_src, tag,
-			    a.collapse_remap, a.collapse_locked);
-			__syncwarp();
-			unsigned mask = __ballot_sync(0xffffffffu, undecided && lane8 == 0);
-			if (mask)
-			{
-				int leader = __ffs(mask) - 1;
-				u32 off = 0;
-				if (int(lane) == leader)
-					off = atomicAdd(counter, u32(__popc(mask)));
-				off = __shfl_sync(0xffffffffu, off, leader);
-				if (undecided && lane8 == 0)
-					next[off + __popc(mask & ((1u << lane) - 1))] = k;
-			}
-		}
+			vstate[(round + 1) % 3] = 0; // last read after the barrier of round - 2
+		if (n <= gsize / 4) // at most two candidates per 8-lane group
+			wave_round_groups(a, a.list[(round - 1) & 1], n, a.list[round & 1], a.state + round % 3, tag, gtid, gsize);
+		else
+			wave_round(a, a.list[(round - 1) & 1], n, a.list[round & 1], a.state + round % 3, tag, gtid, gsize);
 		grid.sync();
 		if (a.round_log && gtid == 0 && round < 256)
 		{
@@ -1251,18 +1409,41 @@ static __global__ void __launch_bounds__(WAVE_THREADS, 1) k_wave_rounds(WaveArgs
 			a.round_log[round * 2] = n;
 			a.round_log[round * 2 + 1] = u32(t);
 		}
-		n = *reinterpret_cast<volatile u32*>(counter);
-		if (n == 0 || round >= a.max_rounds)
-			break;
-		cur = next;
+		n = vstate[round % 3];
+	}
+	if (tail)
+	{
+		// every CTA took the same decision (n was read after a grid barrier): the others are done, CTA 0 finishes alone
+		if (blockIdx.x != 0)
+			return;
+		while (n != 0 && round < a.max_rounds)
+		{
+			++round;
+			++tag;
+			items += n;
+			if (threadIdx.x == 0)
+				vstate[(round + 1) % 3] = 0;
+			wave_round_groups(a, a.list[(round - 1) & 1], n, a.list[round & 1], a.state + round % 3, tag, threadIdx.x, blockDim.x);
+			__threadfence();
+			__syncthreads();
+			if (a.round_log && threadIdx.x == 0 && round < 256)
+			{
+				unsigned long long t;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+				a.round_log[round * 2] = n | 0x80000000u;
+				a.round_log[round * 2 + 1] = u32(t);
+			}
+			n = vstate[round % 3];
+			__syncthreads(); // nobody resets the counter of round + 2 (== round - 1) before everybody has read this one
+		}
 	}
 	if (gtid == 0)
 	{
-		a.state[2] = tag;
-		a.state[3] = round;
-		a.state[4] = n;
-		a.state[5] += round;
-		a.state[6] = a.state[6] > round ? a.state[6] : round;
+		a.state[3] = tag;
+		a.state[4] = round;
+		a.state[5] = n;
+		a.state[6] += round;
+		a.state[7] = a.state[7] > round ? a.state[7] : round;
 		*reinterpret_cast<unsigned long long*>(a.state + 8) = items;
 	}
 }
@@ -2310,8 +2491,9 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 	u32* adj_corner = temp.alloc<u32>(corners);
 	u32* collapse_remap = temp.alloc<u32>(vertex_count);
 	u8* collapse_locked = temp.alloc<u8>(vertex_count);
-	u64* vmin_any = temp.alloc<u64>(vertex_count);
-	u64* vmin_src = temp.alloc<u64>(vertex_count);
+	// per-vertex minima of the wavefront; the CUDA kernel double-buffers them by round parity
+	u64* vmin_any = temp.alloc<u64>(size_t(vertex_count) * 2);
+	u64* vmin_src = temp.alloc<u64>(size_t(vertex_count) * 2);
 	float* group_min = temp.alloc<float>(size_t(G) * 3);
 	float* group_extent = temp.alloc<float>(G);
 	u32* group_collapses = temp.alloc<u32>(G);
@@ -2398,8 +2580,8 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 	u32* flip_flag = temp.alloc<u32>(corners);
 	u64* tagged_error = temp.alloc<u64>(corners);
 
-	dev_memset(vmin_any, 0xff, size_t(vertex_count) * 8);
-	dev_memset(vmin_src, 0xff, size_t(vertex_count) * 8);
+	dev_memset(vmin_any, 0xff, size_t(vertex_count) * 16);
+	dev_memset(vmin_src, 0xff, size_t(vertex_count) * 16);
 	u32* wave_state = temp.alloc<u32>(12);
 	dev_memset(wave_state, 0, 12 * sizeof(u32));
 #ifndef CLODB_EMU
@@ -2444,13 +2626,18 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 
 		u32 rounds = 0;
 		LAUNCH(k_window_init, G, groups, G);
+		ArenaScope pass_scope(temp);
+#ifdef CLODB_EMU
 		u32* wave_list[2] = {tri_weight, flip_flag}; // the cut-scan inputs are not live during the rounds: reuse them as work lists
+#else
+		WaveEntry* wave_list[2] = {temp.alloc<WaveEntry>(cand_total), temp.alloc<WaveEntry>(cand_total)};
+#endif
 		for (;;)
 		{
 			// ---- wavefront over the current windows
-			dev_memset(wave_state, 0, 2 * sizeof(u32));
-			LAUNCH(k_wave_window, (size_t(cand_total) + 31) / 32 * 32, sort_val, cand_group, groups, status, wave_list[0], wave_state, cand_total);
+			dev_memset(wave_state, 0, 3 * sizeof(u32));
 #ifdef CLODB_EMU
+			LAUNCH(k_wave_window, (size_t(cand_total) + 31) / 32 * 32, sort_val, cand_group, groups, status, wave_list[0], wave_state, cand_total);
 			u32 listed = dev_read(wave_state);
 			for (u32 r = 0; listed != 0; )
 			{
@@ -2466,12 +2653,16 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 #else
 			{
 				WaveArgs wa;
-				wa.sorted_cand = sort_val, wa.status = status, wa.cand_v0 = cand_v0, wa.cand_v1 = cand_v1, wa.remap = remap, wa.wedge = wedge, wa.kind = kind, wa.loop = loop, wa.loopback = loopback;
-				wa.vpos = vpos, wa.idx = idx, wa.adj_off = adj_off, wa.adj_corner = adj_corner, wa.vmin_any = vmin_any, wa.vmin_src = vmin_src, wa.collapse_remap = collapse_remap, wa.collapse_locked = collapse_locked;
+				wa.status = status, wa.cand_v0 = cand_v0, wa.cand_v1 = cand_v1, wa.remap = remap, wa.wedge = wedge, wa.kind = kind, wa.loop = loop, wa.loopback = loopback;
+				wa.vpos = vpos, wa.idx = idx, wa.adj_off = adj_off, wa.adj_corner = adj_corner, wa.collapse_remap = collapse_remap, wa.collapse_locked = collapse_locked;
+				wa.vmin_any[0] = vmin_any, wa.vmin_any[1] = vmin_any + vertex_count;
+				wa.vmin_src[0] = vmin_src, wa.vmin_src[1] = vmin_src + vertex_count;
 				wa.list[0] = wave_list[0];
 				wa.list[1] = wave_list[1];
 				wa.state = wave_state;
-				wa.cand_total = cand_total, wa.max_rounds = config_max_rounds();
+				wa.max_rounds = config_max_rounds();
+				static const u32 tail_threshold = getenv("CLODB200_WAVE_TAIL") ? u32(atoi(getenv("CLODB200_WAVE_TAIL"))) : 256u;
+				wa.tail_threshold = tail_threshold;
 				static const bool log_rounds = getenv("CLODB200_DEBUG_ROUNDS") != nullptr;
 				wa.round_log = nullptr;
 				if (log_rounds)
@@ -2480,7 +2671,8 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 					dev_memset(wa.round_log, 0, 512 * 4);
 				}
 				static const u32 blocks_per_sm_cap = getenv("CLODB200_WAVE_BLOCKS") ? u32(atoi(getenv("CLODB200_WAVE_BLOCKS"))) : 0u;
-				u32 blocks = std::min<u32>(blocks_per_sm_cap ? std::min(wave_max_blocks, blocks_per_sm_cap) : wave_max_blocks, (cand_total + WAVE_THREADS / 8 - 1) / (WAVE_THREADS / 8));
+				LAUNCH_GRID(k_wave_list, (cand_total + 255) / 256, 256, sort_val, cand_group, groups, status, cand_v0, cand_v1, remap, wa, cand_total);
+				u32 blocks = std::min<u32>(blocks_per_sm_cap ? std::min(wave_max_blocks, blocks_per_sm_cap) : wave_max_blocks, (cand_total + WAVE_THREADS - 1) / WAVE_THREADS);
 				LAUNCH_COOP(k_wave_rounds, blocks, WAVE_THREADS, wa);
 				if (g_profile)
 				{
@@ -2492,7 +2684,7 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 					std::vector<u32> lg = dev_download(wa.round_log, 512);
 					fprintf(stderr, "wave T %u cands %u blocks %u:", cur_T, cand_total, blocks);
 					for (u32 r = 1; r < 256 && lg[r * 2]; ++r)
-						fprintf(stderr, " %u/%.0fus", lg[r * 2], r > 1 ? (lg[r * 2 + 1] - lg[r * 2 - 1]) / 1e3 : 0.0);
+						fprintf(stderr, " %u%s/%.0fus", lg[r * 2] & 0x7fffffffu, (lg[r * 2] >> 31) ? "t" : "", r > 1 ? (lg[r * 2 + 1] - lg[r * 2 - 1]) / 1e3 : 0.0);
 					fprintf(stderr, "\n");
 				}
 			}
@@ -2554,8 +2746,8 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 #ifndef CLODB_EMU
 	{
 		std::vector<u32> st = dev_download(wave_state, 8);
-		g_simplify_stats.rounds = st[5];
-		g_simplify_stats.max_rounds = st[6];
+		g_simplify_stats.rounds = st[6];
+		g_simplify_stats.max_rounds = st[7];
 	}
 #endif
 	LAUNCH(k_finalize_output, size_t(cur_T) * 3, idx, sv_global, out.tri, size_t(cur_T) * 3);
