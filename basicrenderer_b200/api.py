@@ -427,6 +427,47 @@ class ClodLib:
         self._lib.clodb200_artifactsSerializeMetadata(*args, buf, n)
         return buf.raw
 
+    # ---- scene batches: the library's own NCCL gather of the metadata blobs (csrc/comm.cu) -------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self._lib.clodb200_commGetUniqueId(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes | None, world_size: int, rank: int):
+        self._lib.clodb200_commInit.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        self._check(self._lib.clodb200_commInit(unique_id, world_size, rank))
+
+    def comm_destroy(self):
+        self._lib.clodb200_commDestroy()
+
+    def gather_begin(self, payload: bytes):
+        """Starts the all-gather of this rank's payload on the library's communication stream; returns a handle."""
+        self._lib.clodb200_commGatherBegin.restype = C.c_void_p
+        self._lib.clodb200_commGatherBegin.argtypes = [C.c_char_p, C.c_size_t]
+        h = self._lib.clodb200_commGatherBegin(payload, len(payload))
+        if not h:
+            raise ClodbError(self._lib.clodb200_last_error().decode() or "clodb200 gather failed")
+        return h
+
+    def gather_end(self, handle):
+        """Waits for a gather and returns the payloads of all ranks, by rank."""
+        L = self._lib
+        L.clodb200_commGatherWait.argtypes = [C.c_void_p]
+        L.clodb200_commGatherGet.restype = C.c_void_p
+        L.clodb200_commGatherGet.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.clodb200_commGatherFree.argtypes = [C.c_void_p]
+        L.clodb200_commWorldSize.restype = C.c_int
+        try:
+            self._check(L.clodb200_commGatherWait(handle))
+            out = []
+            for r in range(L.clodb200_commWorldSize()):
+                n = C.c_size_t()
+                p = L.clodb200_commGatherGet(handle, r, C.byref(n))
+                out.append(C.string_at(p, n.value) if n.value else b"")
+            return out
+        finally:
+            L.clodb200_commGatherFree(handle)
+
     def timer_start(self):
         self._lib.clodb200_timerStart()
 

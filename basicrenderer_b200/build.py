@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "basicrenderer_b200", "csrc")
-SOURCES = ["rt.cu", "remap.cu", "mikk.cu", "clusterize.cu", "bounds.cu", "groups.cu", "partition.cu", "simplify.cu", "output.cu", "dag.cu", "artifacts.cu", "capi.cu"]
+SOURCES = ["rt.cu", "remap.cu", "mikk.cu", "clusterize.cu", "bounds.cu", "groups.cu", "partition.cu", "simplify.cu", "output.cu", "dag.cu", "artifacts.cu", "capi.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 PRODUCT_LIB = os.path.join(ROOT, "basicrenderer_b200", "libclodb200.so")
 EMU_LIB = os.path.join(ROOT, "tests", "emu", "libclodb200_emu.so")
@@ -63,7 +63,7 @@ def build_product(force: bool = False, verbose: bool = False, extra_flags=(), li
     if verbose:
         print("\n".join(outs))
     if jobs or force or not os.path.exists(target_lib):
-        _run([NVCC, "-shared", "-o", target_lib] + objs + ["-lcudart"])
+        _run([NVCC, "-shared", "-o", target_lib] + objs + ["-lcudart", "-ldl"])
     return target_lib
 
 
@@ -83,7 +83,7 @@ def build_emu(force: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(_run, jobs))
     if jobs or force or not os.path.exists(EMU_LIB):
-        _run(["g++", "-shared", "-o", EMU_LIB] + objs)
+        _run(["g++", "-shared", "-o", EMU_LIB] + objs + ["-ldl"])
     return EMU_LIB
 
 

@@ -14,6 +14,8 @@
 // pages, so writing the mesh pages directly gives the same bytes.
 #include "artifacts.h"
 
+#include <chrono>
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -1213,8 +1215,20 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	config.simplify_error_merge_previous = std::max(0.0f, settings.lod_error_merge_previous);
 	config.partition_size = std::max<u32>(384u, std::max<u32>(1u, settings.partition_size_floor));
 
+	// CLODB200_LEVEL_TIMES: host wall time of the outer stages on stderr (diagnostics only)
+	const bool trace = getenv("CLODB200_LEVEL_TIMES") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!trace)
+			return;
+		dev_sync();
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "artifacts: %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
 	ArtifactSink sink;
 	build_dag(config, geo.mesh, geo.indices, geo.index_count, ws, sink, stats);
+	lap("DAG build");
 	const u32 M = u32(sink.meshlets.size()), G = u32(sink.groups.size());
 	if (M == 0 || G == 0)
 		throw Error("clodb200: the DAG build produced no groups");
@@ -1312,6 +1326,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		triangle_total += r.tri_count;
 	}
 
+	lap("bucket order + jobs (host)");
 	// ---- device pre-pass: distinct vertices per group, UV ranges per meshlet
 	MeshletJob* d_jobs = temp.alloc<MeshletJob>(M);
 	dev_h2d(d_jobs, jobs.data(), size_t(M) * sizeof(MeshletJob));
@@ -1337,6 +1352,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	if (U)
 		uv_ranges = dev_download(d_uv_ranges, size_t(M) * U * 4);
 
+	lap("meshlet pre-pass + read-back");
 	// per-(meshlet, set) UV compression parameters (CLU.cpp:1268-1306)
 	std::vector<UvJob> uv_jobs(size_t(M) * U);
 	std::vector<u32> uv_bits_total(size_t(M) * U); // totalUvBits / vertex = bitsU + bitsV
@@ -1560,6 +1576,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	}
 	page_ref_offsets.push_back(u32(page_refs.size()));
 
+	lap("pages/segments/hierarchy (host)");
 	// ---- page bytes on the device, one read-back
 	const size_t total_bytes = size_t(page_offsets.back());
 	u8* d_out = temp.alloc<u8>(total_bytes);
@@ -1575,8 +1592,10 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 #else
 	LAUNCH_GRID(k_write_pages_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors);
 #endif
+	lap("page writer kernel");
 	out.pages.reserve(total_bytes + 16);
 	dev_d2h(out.pages.base, d_out, total_bytes);
+	lap("page read-back");
 	out.page_bytes = total_bytes;
 	if (dev_read(d_errors))
 		throw Error("clodb200: page writer found an inconsistent meshlet");

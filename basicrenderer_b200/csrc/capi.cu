@@ -174,6 +174,21 @@ void ensure_thread_context()
 	t_context_ready = true;
 }
 
+} // namespace
+namespace clodb
+{
+// comm.cu reports through the same per-thread error slot
+void capi_set_error(const std::string& message)
+{
+	t_last_error = message;
+}
+bool capi_initialized()
+{
+	return g_initialized;
+}
+} // namespace clodb
+namespace
+{
 template <typename F>
 int guarded(F&& body)
 {

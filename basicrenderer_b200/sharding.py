@@ -81,6 +81,20 @@ def gather_metadata(mesh_ids: Sequence[int], blobs: Sequence[bytes], device=None
     return dict(sorted(merged.items()))
 
 
+def gather_metadata_begin(lib, mesh_ids: Sequence[int], blobs: Sequence[bytes]):
+    """The product path on GPUs: the library's own NCCL all-gather (csrc/comm.cu, clodb200_commGatherBegin) on its communication
+    stream. Returns a handle; the caller keeps building and collects the merged dict later with gather_metadata_end."""
+    return lib.gather_begin(pack_blobs(mesh_ids, blobs))
+
+
+def gather_metadata_end(lib, handle):
+    merged = {}
+    for payload in lib.gather_end(handle):
+        if payload:
+            merged.update(unpack_blobs(payload))
+    return dict(sorted(merged.items()))
+
+
 def dag_summary_blob(rec) -> bytes:
     """Compact per-mesh summary of a recorded DAG build (clodBuildEx level): per group {depth, simplified bounds[5], cluster
     count}. The artifacts path gathers the reference's full metadata blob instead (ClodLib.serialize_metadata,

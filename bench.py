@@ -4,9 +4,13 @@
   python bench.py --gpus N --steps K --warmup W            this framework (CUDA, one process per GPU)
   python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
 
-A step is one full DAG build of the workload mesh (N = 1: config C2, the 10 M-triangle displaced heightfield). Under
-torchrun (N > 1) every rank builds its own shard of a scene batch of independent meshes (config C4 shape, weak scaling);
-there is no data-path collective, only the barrier and the max-over-ranks of the timing.
+A step is one full DAG build of the workload mesh. N = 1: config C3, the 100 M-triangle noisy displaced icosphere with UV
+seams, the mesh the >= 50x target of BASELINE.json is quoted on and the largest single-GPU configuration
+(CLODB200_BENCH_WORKLOAD=C2 selects the 10 M-triangle heightfield, =C4 the scene batch). Under torchrun (N > 1) every rank
+builds its own mesh of that class (independent meshes sharded by mesh: weak scaling); there is no data-path collective, only
+the gather of the per-mesh cache metadata blobs (the library's own NCCL all-gather on a side stream, csrc/comm.cu), the
+barrier and the max-over-ranks of the timing. The line also carries, at N = 1, the C2 measurement ("also"), a parity block
+(our DAG next to the reference's on the CPU arm's sample mesh) and the CPU baseline.
 
 A build is the reference's outer builder call (BuildClusterLODArtifactsFromGeometry, ClusterLODUtilities.cpp:5325, mesh
 mode): DAG to a single root cluster + group tables + traversal hierarchy + mesh-wide page packing, finished
@@ -82,6 +86,15 @@ except Exception:
     pass
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel of ONE build step (one `ncu --metrics` pass, committed under
+# profiles/): {"C2": {"bytes": ..., "source": ...}, ...}
+WHOLE_STEP_DRAM = {}
+try:
+    WHOLE_STEP_DRAM = json.load(open(os.path.join(ROOT, "profiles", "whole_step_dram.json")))
+except Exception:
+    pass
+
+
 def _kernel_table(rows, peak_gbs, limit=10):
     """Top kernels of one profiled step: time, launches and, where DESIGN.md has a byte model for the kernel, the algorithmic
     GB/s and its fraction of the measured HBM peak. rows: (kernel, launches, total_ms, total_threads_or_items)."""
@@ -130,15 +143,36 @@ def _dist():
     return rank, world, local
 
 
-WORKLOAD = os.environ.get("CLODB200_BENCH_WORKLOAD", "C2").upper()  # "C3": the 100 M-triangle seamed icosphere (opt-in, N = 1)
+WORKLOAD = os.environ.get("CLODB200_BENCH_WORKLOAD", "C3").upper()  # C3 (default) | C2 | C4 (scene batch, see run_scene_batch)
 C3_F = 2236  # icosphere frequency => 99 993 920 triangles
+METRIC = "Mtris/s full cluster-LOD DAG build"
 
 
-def _workload(rank: int, world: int):
-    """N = 1: the C2 heightfield. N > 1: mesh `rank` of a batch of equally sized heightfields with distinct noise seeds
-    (weak scaling: per-GPU work is fixed; meshes are independent, the C4 sharding rule).
-    Returns (mesh, tangents or None)."""
-    if WORKLOAD == "C3":
+def _workload_text(workload: str, world: int) -> str:
+    if workload == "C3":
+        f = int(os.environ.get("CLODB200_BENCH_ICO_F", C3_F))
+        t = f"C3: {20 * f * f}-triangle noisy displaced icosphere (f={f}) with normals + per-face UV atlas seams, 7 simplification attributes (normal + tangent xyz + sign), full DAG to a single root cluster; MikkTSpace tangents generated inside the timed call, as in the reference"
+    else:
+        n = int(os.environ.get("CLODB200_BENCH_GRID", WORKLOAD_N))
+        t = f"C2: {2 * n * n}-triangle displaced heightfield grid (n={n}), pos+normal, full DAG to a single root cluster"
+    return t + ("" if world == 1 else f"; one such mesh per GPU ({world} independent meshes with distinct noise seeds, sharded by mesh)")
+
+
+def _config(workload: str, world: int) -> dict:
+    """Names the workload; identical in both arms (`--impl reference` times the reference's CPU implementation on this config)."""
+    return {
+        "workload": _workload_text(workload, world),
+        "builder": "clodDefaultConfig(128) + BasicRenderer overrides (128/128/64, partition 384, 8 refined ids, spatial clusters)",
+        "scope": "BuildClusterLODArtifactsFromGeometry, mesh mode: remap, clusterize, partition, lock, simplify, bounds, error rule, group tables, traversal hierarchy, mesh page packing, page blobs in host memory",
+        "l2": "inputs and per-level working sets (>= 240 MB) exceed the 126 MB L2; no explicit flush",
+    }
+
+
+def _make_mesh(workload: str, rank: int, world: int):
+    """The rank's mesh: (vertices [V, stride/4] f32, indices u32, flags)."""
+    from basicrenderer_b200 import artifacts as art
+
+    if workload == "C3":
         f = int(os.environ.get("CLODB200_BENCH_ICO_F", C3_F))
         # the generator's analytic tangents are not used: the MikkTSpace tangent stream is generated inside every build call
         # (csrc/mikk.cu), as the reference generates it inside BuildClusterLODArtifactsFromGeometry
@@ -146,10 +180,11 @@ def _workload(rank: int, world: int):
         import torch
 
         torch.cuda.empty_cache()
-        return mesh, None
+        return mesh.vertices, mesh.indices, art.VERTEX_NORMALS | art.VERTEX_TEXCOORDS, mesh.triangle_count
     seed = 1234 if world == 1 else 1234 + rank
     n = int(os.environ.get("CLODB200_BENCH_GRID", WORKLOAD_N))
-    return meshgen.grid(n, seed=seed), None
+    m = meshgen.grid(n, seed=seed)
+    return art.interleave(m.positions, m.normals), m.indices, art.VERTEX_NORMALS, m.triangle_count
 
 
 def _pin(a: np.ndarray) -> np.ndarray:
@@ -161,6 +196,74 @@ def _pin(a: np.ndarray) -> np.ndarray:
 
 
 _PINNED = []
+
+
+def _comm_setup(lib, rank, world):
+    """The library's own NCCL communicator for the metadata gather: rank 0 makes the id, torch.distributed only ships it."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+
+    box = [lib.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    lib.comm_init(box[0], world, rank)
+
+
+def _timed_builds(lib, steps, build_once, rank, world):
+    """K builds; with N > 1 each build's metadata blob is gathered to every rank by the library's asynchronous NCCL gather, one
+    batch behind the builds (the last gather is waited for inside the timed region). Returns (device ms, last record)."""
+    from basicrenderer_b200 import sharding
+
+    pending = None
+    lib.timer_start()
+    rec = None
+    for _ in range(steps):
+        rec = build_once(world > 1)
+        if world > 1:
+            blob = lib.serialize_metadata(rec, f"clod_mesh{rank}.clodbin", "bench", f"/mesh{rank}")
+            lib.free_artifacts(rec)
+            h = sharding.gather_metadata_begin(lib, [rank], [blob])
+            if pending is not None:
+                assert len(sharding.gather_metadata_end(lib, pending)) == world
+            pending = h
+    if pending is not None:
+        assert len(sharding.gather_metadata_end(lib, pending)) == world
+    return lib.timer_stop_ms(), rec
+
+
+def _measure(lib, workload, rank, world, steps, warmup, barrier, with_clocks=True):
+    """Resident-input loop (`value`) and host-buffer loop (`e2e`) on this rank's mesh of `workload`."""
+    vertices, indices, flags, T = _make_mesh(workload, rank, world)
+    vertices = _pin(vertices)
+    indices = _pin(indices)
+    handle = lib.upload_geometry(vertices, indices, flags)
+    for _ in range(warmup):
+        rec = lib.build_artifacts_resident(handle, views=True)
+    stop = threading.Event()
+    clock_samples = []
+    sampler = threading.Thread(target=_sample_clocks, args=(stop, clock_samples), daemon=True)
+    if with_clocks:
+        sampler.start()
+    barrier()
+    launches0 = lib.launch_count
+    ms, rec_last = _timed_builds(lib, steps, lambda keep: lib.build_artifacts_resident(handle, views=True, keep_handle=keep), rank, world)
+    launches = lib.launch_count - launches0
+    barrier()
+    if world > 1:  # the gathered runs freed their records; one more (untimed) build for the output statistics
+        rec_last = lib.build_artifacts_resident(handle, views=True)
+    stat = dict(rec_last.stat)
+    # ---- end to end through the host-pointer C ABI (upload + build + page read-back every step)
+    for _ in range(min(warmup, 2)):
+        lib.build_artifacts(vertices, indices, flags, views=True)
+    barrier()
+    ms_e2e, rec_e2e = _timed_builds(lib, steps, lambda keep: lib.build_artifacts(vertices, indices, flags, views=True, keep_handle=keep), rank, world)
+    barrier()
+    if with_clocks:
+        stop.set()
+        sampler.join()
+    d2h = int(stat["d2h_bytes"])
+    return {"T": T, "ms": ms, "ms_e2e": ms_e2e, "launches": launches, "stat": stat, "h2d": vertices.nbytes + indices.nbytes, "d2h": d2h, "clocks": clock_samples,
+            "handle": handle}
 
 
 def run_scene_batch(args):
@@ -179,6 +282,7 @@ def run_scene_batch(args):
     from basicrenderer_b200 import load, sharding
 
     lib = load(local)
+    _comm_setup(lib, rank, world)
     count = int(os.environ.get("CLODB200_BENCH_MESHES", 48))
     total = float(os.environ.get("CLODB200_BENCH_BATCH_TRIS", 48e6))
     budgets = meshgen.scene_batch_sizes(count, total)
@@ -215,7 +319,8 @@ def run_scene_batch(args):
     def step(resident):
         done = [r for lane_out in pool.map(lambda lane: build_lane(lane, resident), lanes) for r in lane_out]
         done.sort()
-        gathered = sharding.gather_metadata([i for i, _ in done], [b for _, b in done])
+        # one gather per batch, through the library's own NCCL all-gather (csrc/comm.cu)
+        gathered = sharding.gather_metadata_end(lib, sharding.gather_metadata_begin(lib, [i for i, _ in done], [b for _, b in done]))
         assert len(gathered) == count
         return sum(len(b) for b in gathered.values())
 
@@ -268,6 +373,7 @@ def run_scene_batch(args):
         lib.free_geometry(h)
     if world > 1:
         dist.barrier()
+        lib.comm_destroy()
         dist.destroy_process_group()
 
 
@@ -282,63 +388,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    from basicrenderer_b200 import load, sharding
+    from basicrenderer_b200 import load
 
     lib = load(local)
-    mesh, tangents = _workload(rank, world)
-    T = mesh.triangle_count
-    from basicrenderer_b200 import artifacts as art
-
-    if WORKLOAD != "C3":
-        vertices = _pin(art.interleave(mesh.positions, mesh.normals))
-        flags = art.VERTEX_NORMALS
-    else:
-        vertices = _pin(mesh.vertices)  # pos + normal + uv, 32-byte stride
-        flags = art.VERTEX_NORMALS | art.VERTEX_TEXCOORDS
-    indices = _pin(mesh.indices)
+    _comm_setup(lib, rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input timing (value)
-    handle = lib.upload_geometry(vertices, indices, flags, tangents=tangents)
-    for _ in range(args.warmup):
-        rec = lib.build_artifacts_resident(handle, views=True)
-    stop = threading.Event()
-    clock_samples = []
-    sampler = threading.Thread(target=_sample_clocks, args=(stop, clock_samples), daemon=True)
-    sampler.start()
-    barrier()
-    launches0 = lib.launch_count
-    lib.timer_start()
-    for _ in range(args.steps):
-        rec = lib.build_artifacts_resident(handle, views=True, keep_handle=world > 1)
-        if world > 1:
-            # the path's only exchange: per-mesh cache metadata (SerializeMetadata bytes) to every rank (NCCL all-gather of
-            # sizes + padded blobs); the page payloads stay with the rank that built them
-            blob = lib.serialize_metadata(rec, f"clod_mesh{rank}.clodbin", "bench", f"/mesh{rank}")
-            lib.free_artifacts(rec)
-            gathered = sharding.gather_metadata([rank], [blob])
-            assert len(gathered) == world
-    ms = lib.timer_stop_ms()
-    launches = lib.launch_count - launches0
-    barrier()
-    stop.set()
-    sampler.join()
-
-    # ---- end to end through the host-pointer C ABI (upload + build + page read-back every step)
-    for _ in range(min(args.warmup, 2)):
-        lib.build_artifacts(vertices, indices, flags, tangents=tangents, views=True)
-    barrier()
-    lib.timer_start()
-    for _ in range(args.steps):
-        rec_e2e = lib.build_artifacts(vertices, indices, flags, tangents=tangents, views=True)
-    ms_e2e = lib.timer_stop_ms()
-    barrier()
-    h2d = vertices.nbytes + indices.nbytes + (tangents.nbytes if tangents is not None else 0)
-    d2h = int(rec_e2e.stat["d2h_bytes"])
+    m = _measure(lib, WORKLOAD, rank, world, args.steps, args.warmup, barrier)
+    ms, ms_e2e, T = m["ms"], m["ms_e2e"], m["T"]
 
     # ---- max over ranks
     if world > 1:
@@ -355,7 +416,7 @@ def run_ours(args):
     if rank == 0:
         # ---- per-kernel breakdown of one more step, CUDA events on the build stream (not part of the timed region)
         lib.profile_enable(True)
-        lib.build_artifacts_resident(handle, views=True)
+        lib.build_artifacts_resident(m["handle"], views=True)
         rows = lib.profile_report()
         lib.profile_enable(False)
         total_kernel_ms = sum(r[2] for r in rows)
@@ -372,30 +433,32 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         bpt = KERNEL_BYTES_PER_THREAD.get(top[0])
         achieved = (bpt * top[3] / (top[2] * 1e-3) / 1e9) if bpt else None
+        traffic = KERNEL_DRAM_TRAFFIC.get(top[0])
         roofline = {
             "bound": "hbm",
             "kernel": top[0],
             "achieved": achieved,
             "peak": peak,
-            "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+            "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
             "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None,
-            "traffic": KERNEL_DRAM_TRAFFIC.get(top[0]),
+            "traffic": traffic.get(WORKLOAD) if isinstance(traffic, dict) else traffic,
             "traffic_source": KERNEL_DRAM_TRAFFIC_SOURCE if top[0] in KERNEL_DRAM_TRAFFIC else None,
             "algorithmic_bytes_per_launch": (bpt * top[3] / max(1, top[1])) if bpt else None,
             "kernel_share_of_step": top[2] / total_kernel_ms if total_kernel_ms else None,
             "launches": top[1],
             "avg_launch_us": top[2] * 1e3 / max(1, top[1]),
-            "top_kernels": _kernel_table(rows, peak),
+            "whole_step_dram": WHOLE_STEP_DRAM.get(WORKLOAD),
+            "top_kernels": _kernel_table(rows, peak, limit=15),
         }
+        lib.free_geometry(m["handle"])
+        m["handle"] = None
 
-        cpu = cpu_baseline_sample()
         ms_per_step = ms / args.steps
-        value = total_tris / (ms_per_step * 1e-3) / 1e6
-        e2e_value = total_tris / (ms_e2e / args.steps * 1e-3) / 1e6
+        stat = m["stat"]
         result = {
-            "metric": "Mtris/s full cluster-LOD DAG build",
-            "value": value,
+            "metric": METRIC,
+            "value": total_tris / (ms_per_step * 1e-3) / 1e6,
             "unit": "Mtris/s",
             "n_gpus": world,
             "steps": args.steps,
@@ -406,31 +469,28 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "f32+u32",
             "data": "synthetic",
-            "config": {
-                "workload": (f"C2: {T}-triangle displaced heightfield grid (n={int(round((T / 2) ** 0.5))}), pos+normal, full DAG to a single root cluster" if WORKLOAD != "C3" else
-                             f"C3: {T}-triangle noisy displaced icosphere (f={int(round((T / 20) ** 0.5))}) with normals + per-face UV atlas seams, 7 simplification attributes (normal + tangent xyz + sign), "
-                             "full DAG to a single root cluster; MikkTSpace tangents generated inside the timed call, as in the reference")
-                            + ("" if world == 1 else f"; one such mesh per GPU ({world} independent meshes, sharded by mesh)"),
-                "builder": "clodDefaultConfig(128) + BasicRenderer overrides (128/128/64, partition 384, 8 refined ids, spatial clusters)",
-                "l2": "inputs and per-level working sets (>= 240 MB) exceed the 126 MB L2; no explicit flush",
-                "levels": rec.stat["levels"],
-                "groups": rec.stat["groups"],
-                "clusters": rec.stat["meshlets"],
-                "segments": rec.stat["segments"],
-                "pages": rec.stat["pages"],
-                "page_bytes": rec.stat["page_bytes"],
-                "scope": "BuildClusterLODArtifactsFromGeometry, mesh mode: remap, clusterize, partition, lock, simplify, bounds, error rule, group tables, traversal hierarchy, mesh page packing, page blobs read back to host",
-                "whole_job_roofline": _whole_job_roofline(rec.stat, T, ms / args.steps, peak, 24 if WORKLOAD != "C3" else 48),
-            },
-            "clocks": _clock_summary(clock_samples),
-            "e2e": {"value": e2e_value, "unit": "Mtris/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
+            "config": _config(WORKLOAD, world),
+            "output": {k: stat[k] for k in ("levels", "groups", "meshlets", "segments", "pages", "page_bytes")},
+            "whole_job_roofline": _whole_job_roofline(stat, T, ms / args.steps, peak, 24 if WORKLOAD != "C3" else 48),
+            "clocks": _clock_summary(m["clocks"]),
+            "e2e": {"value": total_tris / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches": int(m["launches"]),
             "roofline": roofline,
-            "cpu_baseline": cpu,
         }
-    lib.free_geometry(handle)
+        if world == 1:
+            if WORKLOAD == "C3" and not os.environ.get("CLODB200_BENCH_SKIP_ALSO"):
+                # the 10 M-triangle heightfield (BASELINE.json configs[1]) in the same run, short loop
+                c2 = _measure(lib, "C2", 0, 1, 5, 3, barrier, with_clocks=False)
+                lib.free_geometry(c2["handle"])
+                result["also"] = {"config": _config("C2", 1)["workload"], "steps": 5, "warmup": 3, "ms_per_step": c2["ms"] / 5, "value": c2["T"] / (c2["ms"] / 5 * 1e-3) / 1e6,
+                                  "e2e": c2["T"] / (c2["ms_e2e"] / 5 * 1e-3) / 1e6, "unit": "Mtris/s", "groups": c2["stat"]["groups"], "meshlets": c2["stat"]["meshlets"], "gpu_launches_per_step": c2["launches"] // 5}
+            result["parity"] = parity_block(lib)
+            result["cpu_baseline"] = cpu_baseline_sample()
+    if m.get("handle"):
+        lib.free_geometry(m["handle"])
     if world > 1:
         dist.barrier()
+        lib.comm_destroy()
         dist.destroy_process_group()
     if result is not None:
         print(json.dumps(result))
@@ -444,32 +504,50 @@ def _whole_job_roofline(stat, T0, ms_per_step, peak_gbs, s_v=24):
     return {"algorithmic_bytes": int(b), "bytes_per_input_triangle": b / T0, "achieved_gbs": gbs, "frac": gbs / peak_gbs}
 
 
-def _reference_sample_mesh():
-    # bounded sample of the workload: a 1 M-triangle tile of the same heightfield generator and density
-    if WORKLOAD == "C3":
-        return meshgen.icosphere(int(os.environ.get("CLODB200_REF_ICO_F", 224)), True, True)
+# ---- CPU arm: the compiled, unmodified reference on the host cores ------------------------------------------------------------
+def _reference_sample_mesh(workload: str = None, index: int = 0):
+    """Bounded sample of the workload: a 1 M-triangle mesh of the same generator (C3: f = 224 icosphere with the same displacement,
+    normals and UV atlas seams; C2: a tile of the same heightfield at the same density). The reference is ~80 % serial per mesh and
+    gets SLOWER per triangle on larger meshes (10 M-triangle C2: 0.226 vs 0.241 Mtris/s on 8 cores), so the sample flatters it."""
+    workload = workload or WORKLOAD
+    if workload == "C3":
+        return meshgen.icosphere(int(os.environ.get("CLODB200_REF_ICO_F", 224)), True, True, seed=42 + index)
     n = int(os.environ.get("CLODB200_REF_GRID", 707))
-    return meshgen.grid(n, seed=1234)
+    return meshgen.grid(n, seed=1234 + index)
 
 
-def _reference_build(m, threads):
+def _reference_build(m, threads, workload: str = None):
     """One call of the reference's own builder (oracle/_ref/libclodref_full.so: the unmodified
     BuildClusterLODArtifactsFromGeometry with its own clodBuildEx, mesh mode) on host arrays; returns seconds inside the call."""
     from oracle import clodfull
 
-    if WORKLOAD == "C3":
+    if (workload or WORKLOAD) == "C3":
         return clodfull.build(m.vertices, m.indices, flags=m.flags, threads=threads).seconds
     v = clodfull.interleave(m.positions, m.normals)
     return clodfull.build(v, m.indices, flags=clodfull.VERTEX_NORMALS, threads=threads).seconds
 
 
-def _reference_sample_text(m, threads, dt):
-    if WORKLOAD == "C3":
-        return (f"{m.triangle_count}-triangle icosphere of the C3 generator (f=224, same displacement, normals and UV atlas seams), unmodified "
-                f"BuildClusterLODArtifactsFromGeometry in mesh mode incl. its MikkTSpace tangent generation, std::thread pool of {threads} in place of oneTBB, {dt:.2f} s per build")
-    return (f"{m.triangle_count}-triangle tile of the C2 heightfield (same generator/density; the reference is ~80 % serial, so Mtris/s is size "
-            f"independent to first order), unmodified BuildClusterLODArtifactsFromGeometry in mesh mode (meshoptimizer v1.0 + clusterlod.h + L3 builder, "
-            f"std::thread pool of {threads} in place of oneTBB), {dt:.2f} s per build; includes the reference's unused VoxelSourceTriangleBVH::Build (SURVEY.md §8a a20)")
+def _reference_sample_text(m, threads, dt, meshes=1):
+    what = (f"{m.triangle_count}-triangle icosphere of the C3 generator (f=224, same displacement, normals and UV atlas seams), incl. the reference's MikkTSpace tangent generation"
+            if WORKLOAD == "C3" else f"{m.triangle_count}-triangle tile of the C2 heightfield (same generator and density)")
+    fan = "" if meshes == 1 else f"; {meshes} such meshes built concurrently (outer parallel-for over meshes, GlTFGeometryExtractor.cpp:1349; inner parallel-for over groups), "
+    return (f"{what}{fan}; unmodified BuildClusterLODArtifactsFromGeometry in mesh mode (meshoptimizer v1.0 + clusterlod.h + L3 builder, std::thread pool of {threads} per mesh "
+            f"in place of oneTBB), {dt:.2f} s per step; includes the reference's unused VoxelSourceTriangleBVH::Build (SURVEY.md §8a a20)")
+
+
+def _reference_step(meshes, cores):
+    """One step of the CPU arm: every mesh of the step built by the reference, all of them concurrently when there are several
+    (the way an importer fans the primitives of one file out over the worker threads). Returns wall seconds."""
+    if len(meshes) == 1:
+        return _reference_build(meshes[0], cores)
+    inner = max(1, cores // len(meshes))
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=_reference_build, args=(m, inner)) for m in meshes]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    return time.perf_counter() - t0
 
 
 def cpu_baseline_sample():
@@ -492,36 +570,60 @@ def cpu_baseline_sample():
         return {"value": None, "unit": "Mtris/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
 
+def parity_block(lib):
+    """Our DAG next to the reference's on the CPU arm's sample mesh (inner boundary, normals as simplification attributes):
+    per-level triangle delta, fallback-group counts and max-error ratio. tests/test_scale_parity.py asserts the same quantities
+    on C1 / C2-sized meshes; tools/noise_floor.py measures how far the reference's own per-level max moves with its input order."""
+    try:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("scale_parity", os.path.join(ROOT, "tools", "scale_parity.py"))
+        sp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(sp)
+        m = _reference_sample_mesh()
+        ours = sp.ours_stats(lib, m)
+        ref = sp.ref_stats(m)
+        rows, summary = sp.compare(ours, ref)
+        summary["sample"] = f"{m.triangle_count}-triangle sample mesh of the workload generator (the CPU arm's sample), clodBuildEx boundary, normals x3 weight 1"
+        summary["bars"] = {"triangles_per_level": "+-2 %", "max_error": "reference's own input-order spread is 1.2x-1.9x per level (profiles/r02_reference_noise_floor.txt)"}
+        summary["levels_detail"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k in ("depth", "triangles", "ref_triangles", "delta_pct", "sloppy", "ref_sloppy", "error_ratio")} for r in rows]
+        return summary
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
+
+
 def run_reference(args):
     rank, world, _ = _dist()
     if rank != 0:
         return
-    m = _reference_sample_mesh()
-    threads = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        _reference_build(m, threads)
+    n_meshes = max(1, args.gpus)  # the workload of the N-GPU arm is N independent meshes
+    meshes = [_reference_sample_mesh(index=i) for i in range(n_meshes)]
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        _reference_step(meshes, cores)
     total = 0.0
     for _ in range(args.steps):
-        total += _reference_build(m, threads)
+        total += _reference_step(meshes, cores)
     dt = total / args.steps
-    value = m.triangle_count / dt / 1e6
-    sample = _reference_sample_text(m, threads, dt)
+    tris = sum(m.triangle_count for m in meshes)
+    value = tris / dt / 1e6
+    sample = _reference_sample_text(meshes[0], cores if n_meshes == 1 else max(1, cores // n_meshes), dt, n_meshes)
     print(json.dumps({
         "impl": "reference",
-        "metric": "Mtris/s full cluster-LOD DAG build",
+        "metric": METRIC,
         "value": value,
         "unit": "Mtris/s",
         "n_gpus": args.gpus,
         "steps": args.steps,
-        "warmup": min(args.warmup, 1),
+        "warmup": args.warmup,
         "ms_per_step": dt * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f32+u32",
         "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD if WORKLOAD == 'C3' else 'C2'} workload, reference BuildClusterLODArtifactsFromGeometry (mesh mode) on host cores", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "reference", "sample": sample},
+        "config": _config(WORKLOAD if WORKLOAD != "C4" else "C2", max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

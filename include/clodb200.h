@@ -282,6 +282,28 @@ int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char*
 size_t clodb200_artifactsSerializeMetadata(const clodb200_artifacts* artifacts, const char* container_file_name, const char* source_identifier, const char* prim_path,
     const char* subset_name, uint64_t build_config_hash, void* buffer, size_t capacity);
 
+/* ---- scene batches across the GPUs of one box -------------------------------------------------------------
+ * Meshes are independent: a batch is sharded by mesh (one process per GPU, each calling the build entry points above for its own
+ * meshes; the reference fans primitives out over worker threads the same way, GlTFGeometryExtractor.cpp:1349). The only exchange
+ * is the gather of the per-mesh metadata blobs (clodb200_artifactsSerializeMetadata bytes, CLodCache.cpp:169-207) to every rank:
+ * an NCCL all-gather over NVLink on the library's own communication stream, asynchronous to the caller's builds.
+ *   rank 0: clodb200_commGetUniqueId -> ship the 128 bytes to the other ranks by any means (file, socket, MPI, torch.distributed)
+ *   all   : clodb200_init(device); clodb200_commInit(id, world, rank)        (collective)
+ *   all   : h = clodb200_commGatherBegin(blob, bytes)  ... keep building ...  clodb200_commGatherWait(h);
+ *           clodb200_commGatherGet(h, r, &n) for r in 0..world-1; clodb200_commGatherFree(h)     (collective, same order on all ranks)
+ * World size 1 needs no NCCL (loopback). NCCL is loaded at run time (libnccl.so.2; CLODB200_NCCL_LIB overrides the name). */
+#define CLODB200_COMM_ID_BYTES 128
+typedef struct clodb200_gather clodb200_gather;
+int clodb200_commGetUniqueId(void* out_id);
+int clodb200_commInit(const void* id, int world_size, int rank);
+int clodb200_commWorldSize(void);
+int clodb200_commRank(void);
+void clodb200_commDestroy(void);
+clodb200_gather* clodb200_commGatherBegin(const void* payload, size_t bytes);
+int clodb200_commGatherWait(clodb200_gather* gather);
+const void* clodb200_commGatherGet(const clodb200_gather* gather, int rank, size_t* out_bytes);
+void clodb200_commGatherFree(clodb200_gather* gather);
+
 /* CUDA-event stopwatch on the build stream: Start records an event, Stop records another, synchronises and returns the
  * elapsed device time in milliseconds (bench.py brackets its timed steps with these). */
 void clodb200_timerStart(void);
