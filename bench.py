@@ -207,27 +207,30 @@ def _comm_setup(lib, rank, world):
     box = [lib.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     lib.comm_init(box[0], world, rank)
+    # warm-up exchange: NCCL sets its channels up lazily inside the first collective of a communicator (hundreds of ms)
+    for _ in range(2):
+        lib.gather_end(lib.gather_begin(b"warm-up %d" % rank))
 
 
 def _timed_builds(lib, steps, build_once, rank, world):
-    """K builds; with N > 1 each build's metadata blob is gathered to every rank by the library's asynchronous NCCL gather, one
-    batch behind the builds (the last gather is waited for inside the timed region). Returns (device ms, last record)."""
+    """K builds. With N > 1 the K steps are one scene batch of K meshes per rank: every build's cache metadata blob is kept and
+    the batch ends with ONE gather of all blobs to every rank (the library's NCCL all-gather, csrc/comm.cu), inside the timed
+    region. (A gather per step would make the ranks run in lock step; a gather left pending across builds parks an NCCL kernel
+    on the GPU that waits for the slowest peer and keeps this rank's cooperative kernels from becoming co-resident.)
+    Returns (device ms, last record)."""
     from basicrenderer_b200 import sharding
 
-    pending = None
+    blobs = []
     lib.timer_start()
     rec = None
-    for _ in range(steps):
+    for s in range(steps):
         rec = build_once(world > 1)
         if world > 1:
-            blob = lib.serialize_metadata(rec, f"clod_mesh{rank}.clodbin", "bench", f"/mesh{rank}")
+            blobs.append(lib.serialize_metadata(rec, f"clod_mesh{rank}_{s}.clodbin", "bench", f"/mesh{rank}_{s}"))
             lib.free_artifacts(rec)
-            h = sharding.gather_metadata_begin(lib, [rank], [blob])
-            if pending is not None:
-                assert len(sharding.gather_metadata_end(lib, pending)) == world
-            pending = h
-    if pending is not None:
-        assert len(sharding.gather_metadata_end(lib, pending)) == world
+    if world > 1:
+        gathered = sharding.gather_metadata_end(lib, sharding.gather_metadata_begin(lib, [rank * steps + s for s in range(steps)], blobs))
+        assert len(gathered) == world * steps
     return lib.timer_stop_ms(), rec
 
 

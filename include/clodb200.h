@@ -291,6 +291,8 @@ size_t clodb200_artifactsSerializeMetadata(const clodb200_artifacts* artifacts, 
  *   all   : clodb200_init(device); clodb200_commInit(id, world, rank)        (collective)
  *   all   : h = clodb200_commGatherBegin(blob, bytes)  ... keep building ...  clodb200_commGatherWait(h);
  *           clodb200_commGatherGet(h, r, &n) for r in 0..world-1; clodb200_commGatherFree(h)     (collective, same order on all ranks)
+ * Issue the gather after the rank's last build of the batch: a pending NCCL kernel waits on the GPU for the slowest peer and keeps
+ * this rank's cooperative kernels (which need every SM) from becoming co-resident until it has finished.
  * World size 1 needs no NCCL (loopback). NCCL is loaded at run time (libnccl.so.2; CLODB200_NCCL_LIB overrides the name). */
 #define CLODB200_COMM_ID_BYTES 128
 typedef struct clodb200_gather clodb200_gather;
