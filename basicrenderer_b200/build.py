@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "basicrenderer_b200", "csrc")
-SOURCES = ["rt.cu", "remap.cu", "mikk.cu", "clusterize.cu", "bounds.cu", "groups.cu", "partition.cu", "simplify.cu", "output.cu", "dag.cu", "artifacts.cu", "capi.cu", "comm.cu"]
+SOURCES = ["rt.cu", "remap.cu", "mikk.cu", "clusterize.cu", "bounds.cu", "groups.cu", "partition.cu", "simplify.cu", "output.cu", "dag.cu", "artifacts.cu", "capi.cu", "comm.cu", "cachenames.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 PRODUCT_LIB = os.path.join(ROOT, "basicrenderer_b200", "libclodb200.so")
 EMU_LIB = os.path.join(ROOT, "tests", "emu", "libclodb200_emu.so")

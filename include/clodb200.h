@@ -282,6 +282,16 @@ int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char*
 size_t clodb200_artifactsSerializeMetadata(const clodb200_artifacts* artifacts, const char* container_file_name, const char* source_identifier, const char* prim_path,
     const char* subset_name, uint64_t build_config_hash, void* buffer, size_t capacity);
 
+/* Cache naming: how the renderer finds a cache (CLodCache.cpp:62-80, 586-633). boost::hash_combine chains restated from the
+ * published Boost.ContainerHash (>= 1.82) algorithm; Boost is neither vendored nor installed, so these names are "parity unpinned"
+ * (csrc/cachenames.cu). Each name function returns the byte count incl. the terminator and writes at most `capacity` bytes.
+ *   clodb200_cacheBuildConfigHash  == CLodCache::ComputeBuildConfigHash()                        (reads BASICRENDERER_CLOD_VOXEL_*)
+ *   clodb200_cacheFileName         == CLodCache::BuildCacheFileName(key, hash)                   "clod_<hex>.usdc"
+ *   clodb200_cacheSubdirectory     == BuildSceneCacheSubdirectory(sourceIdentifier)              "clod/<stem>_<hex>" */
+uint64_t clodb200_cacheBuildConfigHash(void);
+size_t clodb200_cacheFileName(const char* source_identifier, const char* prim_path, const char* subset_name, uint64_t build_config_hash, char* out, size_t capacity);
+size_t clodb200_cacheSubdirectory(const char* source_identifier, char* out, size_t capacity);
+
 /* ---- scene batches across the GPUs of one box -------------------------------------------------------------
  * Meshes are independent: a batch is sharded by mesh (one process per GPU, each calling the build entry points above for its own
  * meshes; the reference fans primitives out over worker threads the same way, GlTFGeometryExtractor.cpp:1349). The only exchange
