@@ -263,6 +263,27 @@ class ClodLib:
         self._check(self._lib.clodb200_localIndicesBatch(_ptr(indices), _ptr(offs), C.c_size_t(K), C.c_size_t(vertex_capacity), _ptr(vertices), _ptr(triangles), _ptr(counts)))
         return vertices, triangles, counts
 
+    def protect_bits(self, attributes, protect_mask: int, remap, locks=None) -> np.ndarray:
+        attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+        remap = np.ascontiguousarray(remap, dtype=np.uint32)
+        out = np.zeros(remap.size, np.uint8) if locks is None else np.ascontiguousarray(locks, dtype=np.uint8).copy()
+        self._lib.clodb200_protectBits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t]
+        self._check(self._lib.clodb200_protectBits(_ptr(out), _ptr(attributes), attributes.shape[1] * 4, protect_mask, _ptr(remap), remap.size))
+        return out
+
+    def partition_finish(self, cluster_part, partition_count, cluster_refined, cluster_bounds5, config: Config | None = None):
+        """-> (group_clusters[K], group_offsets[G+1]) for a given partition id per cluster (clusterlod.h:396-507)."""
+        cfg = config or self.builder_config()
+        part = np.ascontiguousarray(cluster_part, dtype=np.uint32)
+        refined = np.ascontiguousarray(cluster_refined, dtype=np.int32)
+        bounds = np.ascontiguousarray(cluster_bounds5, dtype=np.float32)
+        K = part.size
+        clusters = np.zeros(K, np.uint32)
+        offsets = np.zeros(K + 1, np.uint32)
+        count = C.c_size_t(0)
+        self._check(self._lib.clodb200_partitionFinish(C.byref(cfg), _ptr(part), C.c_size_t(int(partition_count)), C.c_size_t(K), _ptr(refined), _ptr(bounds), _ptr(clusters), _ptr(offsets), C.byref(count)))
+        return clusters, offsets[: count.value + 1].copy()
+
     def lock_boundary(self, locks: np.ndarray, indices: np.ndarray, group_index_offsets: np.ndarray, remap: np.ndarray, vertex_lock=None) -> np.ndarray:
         locks = np.ascontiguousarray(locks, dtype=np.uint8).copy()
         indices = np.ascontiguousarray(indices, dtype=np.uint32)

@@ -384,6 +384,32 @@ int clodb200_generatePositionRemap(unsigned int* remap, const float* positions, 
 	});
 }
 
+int clodb200_protectBits(unsigned char* locks, const float* attributes, size_t attributes_stride, unsigned int protect_mask, const unsigned int* remap, size_t vertex_count)
+{
+	return guarded([&]() -> int {
+		if (vertex_count == 0)
+			return CLODB200_OK;
+		if (!locks || !remap || (protect_mask && attributes && (attributes_stride < 4 || attributes_stride % 4)))
+			return fail(CLODB200_ERR_INVALID, "clodb200_protectBits: invalid arguments");
+		for (size_t i = 0; i < vertex_count; ++i)
+			if (remap[i] >= vertex_count)
+				return fail(CLODB200_ERR_INVALID, "clodb200_protectBits: remap entry out of range");
+		ensure_workspace(vertex_count * (attributes_stride + 8) + (1 << 20), 1 << 20);
+		u8* dlocks = g_ws.persist.alloc<u8>(vertex_count);
+		u32* dremap = g_ws.persist.alloc<u32>(vertex_count);
+		dev_h2d(dlocks, locks, vertex_count);
+		dev_h2d(dremap, remap, vertex_count * 4);
+		if (attributes && protect_mask)
+		{
+			float* dattr = g_ws.persist.alloc<float>(vertex_count * (attributes_stride / 4));
+			dev_h2d(dattr, attributes, vertex_count * attributes_stride);
+			protect_bits(dattr, u32(attributes_stride / 4), protect_mask, dremap, vertex_count, dlocks);
+		}
+		dev_d2h(locks, dlocks, vertex_count);
+		return CLODB200_OK;
+	});
+}
+
 int clodb200_generateMikkTangents(const void* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count,
     float* out_tangents4, int* out_generated, float* out_corner_tangents4)
 {
@@ -411,6 +437,36 @@ int clodb200_generateMikkTangents(const void* vertices, size_t vertex_count, uns
 				dev_d2h(out_corner_tangents4, dc, index_count * 16);
 			*out_generated = 1;
 		}
+		return CLODB200_OK;
+	});
+}
+
+int clodb200_partitionFinish(const clodb200_config* config, const unsigned int* cluster_part, size_t partition_count, size_t cluster_count, const int* cluster_refined,
+    const float* cluster_bounds5, unsigned int* out_group_clusters, unsigned int* out_group_offsets, size_t* out_group_count)
+{
+	return guarded([&]() -> int {
+		if (out_group_count)
+			*out_group_count = 0;
+		if (cluster_count == 0 || partition_count == 0)
+			return CLODB200_OK;
+		if (!cluster_part || !cluster_refined || !cluster_bounds5 || !out_group_clusters || !out_group_offsets || !out_group_count)
+			return fail(CLODB200_ERR_INVALID, "clodb200_partitionFinish: invalid arguments");
+		for (size_t c = 0; c < cluster_count; ++c)
+			if (cluster_part[c] >= partition_count)
+				return fail(CLODB200_ERR_INVALID, "clodb200_partitionFinish: partition id out of range");
+		const u32 K = u32(cluster_count);
+		ensure_workspace(size_t(K) * 64 + (16 << 20), size_t(K) * 256 + (16 << 20));
+		u32* d_part = g_ws.persist.alloc<u32>(K);
+		int* d_refined = g_ws.persist.alloc<int>(K);
+		float* d_bounds = g_ws.persist.alloc<float>(size_t(K) * 5);
+		dev_h2d(d_part, cluster_part, size_t(K) * 4);
+		dev_h2d(d_refined, cluster_refined, size_t(K) * 4);
+		dev_h2d(d_bounds, cluster_bounds5, size_t(K) * 20);
+		GroupSet gs = partition_finish(d_part, u32(partition_count), K, d_refined, d_bounds, to_config(config), g_ws);
+		dev_d2h(out_group_clusters, gs.group_clusters, size_t(K) * 4);
+		for (u32 g = 0; g <= gs.group_count; ++g)
+			out_group_offsets[g] = gs.group_cluster_offset_host[g];
+		*out_group_count = gs.group_count;
 		return CLODB200_OK;
 	});
 }

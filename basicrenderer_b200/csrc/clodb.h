@@ -99,6 +99,10 @@ struct GroupSet
 // clod::partition (clusterlod.h:350-510) for the pending clusters of one level (all K clusters of the ClusterSet)
 GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 cluster_count, const int* cluster_refined, const float* cluster_bounds5, const u32* remap, const float* positions, size_t vertex_count, const Config& config, Workspace& ws);
 
+// The deterministic second half of clod::partition (clusterlod.h:396-507) for a GIVEN partition id per cluster (device array):
+// spatial order of the partitions, cluster order inside them, refined-id cap split. "Bit-exact given the same partitions."
+GroupSet partition_finish(const u32* cluster_part, u32 partition_count, u32 cluster_count, const int* cluster_refined, const float* cluster_bounds5, const Config& config, Workspace& ws);
+
 // ---- S5: group assembly + boundary locks (groups.cu) --------------------------------------------------------------
 // Gathers the triangles of each group (clusters listed group-major in group_clusters) into one contiguous run per group,
 // as runIterationTask's merge (clusterlod.h:708-711). Returns the per-group triangle offsets (host) in out_offsets.

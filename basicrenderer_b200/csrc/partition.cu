@@ -1036,6 +1036,90 @@ static bool refined_fits_single_group(const std::vector<int>& refined, u32 cap)
 	return true;
 }
 
+// Second half of clod::partition (clusterlod.h:396-507), given a partition id per cluster: spatial order of the partitions by the
+// centre of their last cluster (meshopt_spatialSortRemap, spatialorder.cpp:218-251), clusters in ascending index inside a
+// partition, then the refined-id cap split. Deterministic given `part`; fills out.group_clusters / group_cluster_offset.
+static void finish_groups(u32* part, const u32* part_last, u32 G, u32 K, const int* cluster_refined, const float* cluster_bounds5, const Config& config, Workspace& ws, u32* scalars, GroupSet& out)
+{
+	Arena& temp = ws.temp;
+	u32 cap = config.partition_max_refined_groups;
+	u32* part_remap = nullptr;
+	if (config.partition_sort)
+	{
+		u32* minmax = scalars + 4;
+		u32 init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+		dev_h2d(minmax, init, sizeof(init));
+		u64* keys = temp.alloc<u64>(G);
+		u64* keys_tmp = temp.alloc<u64>(G);
+		u32* vals = temp.alloc<u32>(G);
+		u32* vals_tmp = temp.alloc<u32>(G);
+		part_remap = temp.alloc<u32>(G);
+		LAUNCH(k_part_points_minmax, G, part_last, cluster_bounds5, G, minmax);
+		LAUNCH(k_part_morton, G, part_last, cluster_bounds5, minmax, G, keys, vals);
+		radix_sort_pairs<u64>(keys, keys_tmp, vals, vals_tmp, G, 0, 50, temp);
+		LAUNCH(k_invert_order, G, vals, part_remap, G);
+	}
+
+	u32* group_offset = temp.alloc<u32>(size_t(G) + 1);
+	u32* part_tmp = temp.alloc<u32>(K);
+	u32* ids_tmp = temp.alloc<u32>(K);
+	dev_memset(group_offset, 0, (size_t(G) + 1) * 4);
+	LAUNCH(k_apply_part_remap, K, part, part_remap, out.group_clusters, group_offset, K);
+	exclusive_scan_u32(group_offset, group_offset, size_t(G) + 1, nullptr, temp);
+	radix_sort_pairs<u32>(part, part_tmp, out.group_clusters, ids_tmp, K, 0, bits_for(G > 1 ? G - 1 : 1), temp);
+
+	// ---- refined-id cap
+	u32* marks = temp.alloc<u32>(size_t(K) + 1);
+	dev_memset(marks, 0, (size_t(K) + 1) * 4);
+	if (cap > 0)
+	{
+		u32* scratch_clusters = temp.alloc<u32>(K);
+#ifdef CLODB_EMU
+		LAUNCH(k_refined_cap, G, group_offset, out.group_clusters, cluster_refined, G, cap, scratch_clusters, marks, scalars + 2);
+#else
+		LAUNCH_GRID(k_refined_cap_warp, (G + 7) / 8, 256, group_offset, out.group_clusters, cluster_refined, G, cap, scratch_clusters, marks, scalars + 2);
+#endif
+	}
+	LAUNCH(k_group_start_flags, G, group_offset, G, marks);
+	u32* marks_scanned = temp.alloc<u32>(size_t(K) + 1);
+	exclusive_scan_u32(marks, marks_scanned, K, scalars, temp);
+	u32 G_final = dev_read(scalars);
+	LAUNCH(k_emit_group_offsets, size_t(K) + 1, marks, marks_scanned, K, G_final, out.group_cluster_offset);
+
+	out.group_count = G_final;
+	out.refined_splits = cap > 0 && G_final != G ? dev_read(scalars + 2) : 0;
+	out.group_cluster_offset_host = dev_download(out.group_cluster_offset, size_t(G_final) + 1);
+	out.merge_rounds = 0;
+}
+
+KERNEL k_part_last(const u32* __restrict__ part, u32* part_last_cluster, u32 K)
+{
+	size_t c = GTID;
+	if (c < K)
+		atomicMax(&part_last_cluster[part[c]], u32(c));
+}
+
+GroupSet partition_finish(const u32* part_in, u32 G, u32 K, const int* cluster_refined, const float* cluster_bounds5, const Config& config, Workspace& ws)
+{
+	GroupSet out;
+	out.cluster_count = K;
+	if (K == 0 || G == 0)
+		return out;
+	Arena& temp = ws.temp;
+	out.group_clusters = ws.persist.alloc<u32>(K);
+	out.group_cluster_offset = ws.persist.alloc<u32>(size_t(K) + 1);
+	ArenaScope scope(temp);
+	u32* scalars = temp.alloc<u32>(16);
+	dev_memset(scalars, 0, 16 * sizeof(u32));
+	u32* part = temp.alloc<u32>(K);
+	u32* part_last = temp.alloc<u32>(G);
+	dev_d2d(part, part_in, size_t(K) * 4);
+	dev_memset(part_last, 0, size_t(G) * 4);
+	LAUNCH(k_part_last, K, part, part_last, K);
+	finish_groups(part, part_last, G, K, cluster_refined, cluster_bounds5, config, ws, scalars, out);
+	return out;
+}
+
 GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K, const int* cluster_refined, const float* cluster_bounds5, const u32* remap, const float* positions, size_t vertex_count, const Config& config, Workspace& ws)
 {
 	GroupSet out;
@@ -1214,53 +1298,7 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 	dev_memset(part_last, 0, size_t(G) * 4);
 	LAUNCH(k_cluster_part, K, label, root_rank, part, part_last, K);
 
-	u32* part_remap = nullptr;
-	if (config.partition_sort)
-	{
-		u32* minmax = scalars + 4;
-		u32 init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
-		dev_h2d(minmax, init, sizeof(init));
-		u64* keys = temp.alloc<u64>(G);
-		u64* keys_tmp = temp.alloc<u64>(G);
-		u32* vals = temp.alloc<u32>(G);
-		u32* vals_tmp = temp.alloc<u32>(G);
-		part_remap = temp.alloc<u32>(G);
-		LAUNCH(k_part_points_minmax, G, part_last, cluster_bounds5, G, minmax);
-		LAUNCH(k_part_morton, G, part_last, cluster_bounds5, minmax, G, keys, vals);
-		radix_sort_pairs<u64>(keys, keys_tmp, vals, vals_tmp, G, 0, 50, temp);
-		LAUNCH(k_invert_order, G, vals, part_remap, G);
-	}
-
-	u32* group_offset = temp.alloc<u32>(size_t(G) + 1);
-	u32* part_tmp = temp.alloc<u32>(K);
-	u32* ids_tmp = temp.alloc<u32>(K);
-	dev_memset(group_offset, 0, (size_t(G) + 1) * 4);
-	LAUNCH(k_apply_part_remap, K, part, part_remap, out.group_clusters, group_offset, K);
-	exclusive_scan_u32(group_offset, group_offset, size_t(G) + 1, nullptr, temp);
-	radix_sort_pairs<u32>(part, part_tmp, out.group_clusters, ids_tmp, K, 0, bits_for(G > 1 ? G - 1 : 1), temp);
-
-	// ---- refined-id cap
-	u32* marks = temp.alloc<u32>(size_t(K) + 1);
-	dev_memset(marks, 0, (size_t(K) + 1) * 4);
-	if (cap > 0)
-	{
-		u32* scratch_clusters = temp.alloc<u32>(K);
-#ifdef CLODB_EMU
-		LAUNCH(k_refined_cap, G, group_offset, out.group_clusters, cluster_refined, G, cap, scratch_clusters, marks, scalars + 2);
-#else
-		LAUNCH_GRID(k_refined_cap_warp, (G + 7) / 8, 256, group_offset, out.group_clusters, cluster_refined, G, cap, scratch_clusters, marks, scalars + 2);
-#endif
-	}
-	LAUNCH(k_group_start_flags, G, group_offset, G, marks);
-	u32* marks_scanned = temp.alloc<u32>(size_t(K) + 1);
-	exclusive_scan_u32(marks, marks_scanned, K, scalars, temp);
-	u32 G_final = dev_read(scalars);
-	LAUNCH(k_emit_group_offsets, size_t(K) + 1, marks, marks_scanned, K, G_final, out.group_cluster_offset);
-
-	out.group_count = G_final;
-	out.refined_splits = cap > 0 && G_final != G ? dev_read(scalars + 2) : 0;
-	out.group_cluster_offset_host = dev_download(out.group_cluster_offset, size_t(G_final) + 1);
-	out.merge_rounds = 0;
+	finish_groups(part, part_last, G, K, cluster_refined, cluster_bounds5, config, ws, scalars, out);
 	return out;
 }
 

@@ -95,6 +95,18 @@ int clodb200_generateMikkTangents(const void* vertices, size_t vertex_count, uns
  * Outputs: cluster_index_counts/cluster_vertex_counts/cluster_segments hold one entry per cluster (capacity
  * index_count / 3 entries each), out_indices receives index_count cluster-major indices. Returns the cluster count in
  * *out_cluster_count. segment_offsets == NULL means one segment covering everything. */
+/* a3: locks[i] |= 2 (meshopt_SimplifyVertex_Protect) where vertex i is not its position class's canonical vertex and one of the
+ * attribute columns selected by protect_mask differs from the canonical vertex's (float !=), clusterlod.h:829-841. */
+int clodb200_protectBits(unsigned char* locks, const float* attributes, size_t attributes_stride, unsigned int protect_mask, const unsigned int* remap, size_t vertex_count);
+
+/* a8: the deterministic second half of clod::partition (clusterlod.h:396-507) for a given partition id per cluster (what
+ * meshopt_partitionClusters returned): partitions ordered by meshopt_spatialSortRemap of their last cluster's centre
+ * (spatialorder.cpp:218-251), clusters in ascending order inside a partition, then the refined-id cap split
+ * (partition_max_refined_groups). cluster_bounds5 = {centre xyz, radius, error} per cluster. out_group_clusters has cluster_count
+ * entries, out_group_offsets cluster_count + 1 (worst case); bit-exact given the same partitions. */
+int clodb200_partitionFinish(const clodb200_config* config, const unsigned int* cluster_part, size_t partition_count, size_t cluster_count, const int* cluster_refined,
+    const float* cluster_bounds5, unsigned int* out_group_clusters, unsigned int* out_group_offsets, size_t* out_group_count);
+
 int clodb200_clusterize(const clodb200_config* config, const unsigned int* indices, size_t index_count, const unsigned int* segment_offsets, size_t segment_count,
     const float* positions, size_t vertex_count, size_t positions_stride,
     unsigned int* cluster_index_counts, unsigned int* cluster_vertex_counts, unsigned int* cluster_segments, unsigned int* out_indices, size_t* out_cluster_count);

@@ -194,3 +194,19 @@ def test_sloppy_fallback_bit_exact(lib, oracle, meshes, name):
         assert np.array_equal(si[so[1] : so[2]], want1), p
         assert se[1] == np.float32(werr1), p
     assert used_fallback >= 2
+
+
+@pytest.mark.parametrize("name", ["ico16uv", "grid64"])
+def test_protect_bits_stage(lib, oracle, ref_dag, meshes, name):
+    """a3 as a stage of its own (clusterlod.h:829-841): the seamed icosphere duplicates positions with different normals along the
+    chart borders (bits set there); masks select attribute columns; -0 == +0 and NaN != NaN follow float comparison."""
+    m = meshes[name]
+    remap = oracle.position_remap(m.positions)
+    assert np.array_equal(lib.protect_bits(m.normals, 7, remap), ref_dag(name).get("protect_locks"))
+    # hand-made classes: vertex 1..4 share vertex 0's position class
+    attrs = np.array([[0.0, 1.0, 2.0], [-0.0, 1.0, 2.0], [0.0, 1.5, 2.0], [0.0, 1.0, np.nan], [0.0, 1.0, 2.0], [9.0, 9.0, 9.0]], np.float32)
+    remap = np.array([0, 0, 0, 0, 0, 5], np.uint32)
+    assert lib.protect_bits(attrs, 7, remap).tolist() == [0, 0, 2, 2, 0, 0]
+    assert lib.protect_bits(attrs, 1, remap).tolist() == [0, 0, 0, 0, 0, 0]  # column 0 only: -0 == +0
+    assert lib.protect_bits(attrs, 2, remap).tolist() == [0, 0, 2, 0, 0, 0]
+    assert lib.protect_bits(attrs, 4, remap, locks=np.array([1, 1, 1, 1, 1, 1], np.uint8)).tolist() == [1, 1, 1, 3, 1, 1]  # bits are OR-ed in
