@@ -428,3 +428,113 @@ def icosphere_seams_torch(f: int, seed: int = 42, device=None, chunk: int = 1 <<
     tris = torch.cat([ltris + fi * npf for fi in range(20)], dim=0).reshape(-1).to(torch.int32)
     mesh = Mesh(verts.cpu().numpy(), tris.cpu().numpy().view(np.uint32), VERTEX_NORMALS | VERTEX_TEXCOORDS, f"icosphere{f}_disp_uv")
     return mesh, tang.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Scene batches at full size (configs C4 / C5: 512 / 4 096 meshes, ~1 B / ~8 B triangles): the same three generators
+# written with torch ops so that a rank can generate its shard on its GPU in seconds (the numpy versions evaluate the value noise
+# on one host core). Same formulas and seeds as grid() / torus() / icosphere(displace=True); float operation order on the GPU is
+# not the CPU's, so these are the same surfaces, not bit-identical vertex streams.
+
+
+def _t_device(device):
+    import torch
+
+    return torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def _t_grid_indices(nx_quads: int, ny_quads: int, row: int, dev, wrap_x: bool = False, wrap_y: bool = False):
+    import torch
+
+    a = torch.arange(nx_quads, device=dev).view(1, -1).expand(ny_quads, nx_quads).reshape(-1)
+    b = torch.arange(ny_quads, device=dev).view(-1, 1).expand(ny_quads, nx_quads).reshape(-1)
+    a1 = (a + 1) % nx_quads if wrap_x else a + 1
+    b1 = (b + 1) % ny_quads if wrap_y else b + 1
+    v00, v10, v01, v11 = b * row + a, b * row + a1, b1 * row + a, b1 * row + a1
+    return torch.stack([v00, v10, v11, v00, v11, v01], dim=1).reshape(-1).to(torch.int32)
+
+
+def grid_torch(n: int, seed: int = 1234, amplitude: float = 0.1, device=None) -> Mesh:
+    import torch
+
+    dev = _t_device(device)
+    m = n + 1
+    xs = torch.arange(m, dtype=torch.float64, device=dev) / n
+    px = xs.view(1, -1).expand(m, m).reshape(-1)
+    py = xs.view(-1, 1).expand(m, m).reshape(-1)
+
+    def height(x, y):
+        z = torch.zeros_like(x)
+        for k in range(4):
+            f = 4.0 * (2**k)
+            pts = torch.stack([x * f, y * f, torch.full_like(x, 0.5 + k)], dim=1)
+            z += amplitude * (0.5**k) * _t_value_noise3(pts, seed + k)
+        return z
+
+    eps = 0.5 / n
+    pz = height(px, py)
+    nx = (height(px + eps, py) - height(px - eps, py)) / (2 * eps)
+    ny = (height(px, py + eps) - height(px, py - eps)) / (2 * eps)
+    nrm = torch.stack([-nx, -ny, torch.ones_like(nx)], dim=1)
+    nrm = nrm / torch.linalg.norm(nrm, dim=1, keepdim=True)
+    verts = torch.cat([torch.stack([px, py, pz], dim=1), nrm], dim=1).float()
+    tris = _t_grid_indices(n, n, m, dev)
+    return Mesh(verts.cpu().numpy(), tris.cpu().numpy().view(np.uint32), VERTEX_NORMALS, f"grid{n}")
+
+
+def torus_torch(nu: int, nv: int, seed: int = 0, major: float = 1.0, minor: float = 0.35, device=None) -> Mesh:
+    import math
+
+    import torch
+
+    dev = _t_device(device)
+    u = torch.arange(nu, dtype=torch.float64, device=dev) / nu * 2 * math.pi
+    v = torch.arange(nv, dtype=torch.float64, device=dev) / nv * 2 * math.pi
+    uu = u.view(1, -1).expand(nv, nu).reshape(-1)
+    vv = v.view(-1, 1).expand(nv, nu).reshape(-1)
+    N = torch.stack([torch.cos(vv) * torch.cos(uu), torch.cos(vv) * torch.sin(uu), torch.sin(vv)], dim=1)
+    Cc = torch.stack([major * torch.cos(uu), major * torch.sin(uu), torch.zeros_like(uu)], dim=1)
+    P = Cc + minor * N
+    P = P + N * (0.01 * _t_value_noise3(P * 6.0 + 50.0, seed)).unsqueeze(1)
+    verts = torch.cat([P, N], dim=1).float()
+    tris = _t_grid_indices(nu, nv, nu, dev, wrap_x=True, wrap_y=True)
+    return Mesh(verts.cpu().numpy(), tris.cpu().numpy().view(np.uint32), VERTEX_NORMALS, f"torus{nu}x{nv}")
+
+
+def icosphere_torch(f: int, seed: int = 42, device=None) -> Mesh:
+    """Welded, displaced icosphere with gradient normals (icosphere(f, displace=True, uv_atlas=False)): the seamed construction with
+    the chart-border duplicates merged by position."""
+    import torch
+
+    dev = _t_device(device)
+    mesh, _ = icosphere_seams_torch(f, seed=seed, device=dev)
+    v = torch.from_numpy(mesh.vertices).to(dev)
+    idx = torch.from_numpy(mesh.indices.view(np.int32).astype(np.int64)).to(dev)
+    key = v[:, 0:3].contiguous().view(torch.int32).long()  # chart borders carry bit-identical positions
+    packed = (key[:, 0] & 0xFFFFFFFF) * 0x9E3779B1 ^ (key[:, 1] & 0xFFFFFFFF) * 0x85EBCA77 ^ (key[:, 2] & 0xFFFFFFFF) * 0xC2B2AE3D
+    # exact weld: unique rows of the three position words
+    _, inverse = torch.unique(key, dim=0, return_inverse=True)
+    del packed
+    count = int(inverse.max()) + 1
+    first = torch.full((count,), v.shape[0], dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, inverse, torch.arange(v.shape[0], device=dev), reduce="amin")
+    order = torch.argsort(first)  # keep first-occurrence vertex order
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(count, device=dev)
+    verts = v[first[order], 0:6].contiguous()
+    tris = rank[inverse[idx]].to(torch.int32)
+    return Mesh(verts.cpu().numpy(), tris.cpu().numpy().view(np.uint32), VERTEX_NORMALS, f"icosphere{f}_disp")
+
+
+def scene_mesh_torch(i: int, target_tris: float, device=None) -> Mesh:
+    """scene_mesh(i, target_tris) generated with torch on `device` (same type rule, sizes and seeds)."""
+    kind = i % 3
+    if kind == 0:
+        f = max(2, int(round((target_tris / 20.0) ** 0.5)))
+        return icosphere_torch(f, seed=i, device=device)
+    if kind == 1:
+        n = max(2, int(round((target_tris / 2.0) ** 0.5)))
+        return grid_torch(n, seed=i, device=device)
+    nu = max(3, int(round((target_tris / 2.0 * 2.0) ** 0.5)))
+    nv = max(3, int(round(target_tris / 2.0 / nu)))
+    return torus_torch(nu, nv, seed=i, device=device)

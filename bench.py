@@ -269,11 +269,65 @@ def _measure(lib, workload, rank, world, steps, warmup, barrier, with_clocks=Tru
             "handle": handle}
 
 
+def _batch_shape():
+    count = int(os.environ.get("CLODB200_BENCH_MESHES", 4096 if WORKLOAD == "C5" else 512))
+    total = float(os.environ.get("CLODB200_BENCH_BATCH_TRIS", 8.0e9 if WORKLOAD == "C5" else 1.0e9))
+    return count, total
+
+
+def _batch_config(world: int) -> dict:
+    count, total = _batch_shape()
+    c = _config("C2", 1)
+    c["workload"] = (f"{WORKLOAD if WORKLOAD in ('C4', 'C5') else 'C4'}: scene batch of {count} independent synthetic meshes (sphere / heightfield / torus by index, pos+normal, log-uniform triangle "
+                     f"budgets rescaled to {total:.3g} triangles in total), every mesh built to a single root cluster, sharded by mesh across the GPUs (LPT), one metadata gather per batch")
+    c["l2"] = "meshes are built back to back, several in flight; the shard (>= 3 GB per GPU) exceeds the 126 MB L2"
+    return c
+
+
+def _reference_batch_step(meshes, cores):
+    """The CPU arm's scene-batch step: the meshes are the primitives of one file - outer parallel-for over meshes
+    (GlTFGeometryExtractor.cpp:1349), each mesh built by the reference's builder with its group-level parallel-for."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    inner = max(1, cores // max(1, min(len(meshes), cores)))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(len(meshes), cores)) as ex:
+        list(ex.map(lambda m: _reference_build(m, inner, "C2"), meshes))
+    return time.perf_counter() - t0
+
+
+def run_reference_batch(args):
+    """Bounded sample of the scene batch for the CPU arm: 2 x cores meshes of the batch's own generator and budget distribution
+    (every k-th mesh of the batch, budgets scaled so that the sample holds CLODB200_REF_BATCH_TRIS triangles, default 6 M)."""
+    count, total = _batch_shape()
+    cores = os.cpu_count() or 1
+    budgets = meshgen.scene_batch_sizes(count, total)
+    take = min(count, 2 * cores)
+    ids = [int(round(k * (count - 1) / max(1, take - 1))) for k in range(take)] if take > 1 else [0]
+    scale = float(os.environ.get("CLODB200_REF_BATCH_TRIS", 6.0e6)) / float(sum(budgets[i] for i in ids))
+    meshes = [meshgen.scene_mesh(i, max(2000.0, budgets[i] * scale)) for i in ids]
+    for _ in range(args.warmup):
+        _reference_batch_step(meshes, cores)
+    dt = sum(_reference_batch_step(meshes, cores) for _ in range(args.steps)) / max(1, args.steps)
+    tris = sum(m.triangle_count for m in meshes)
+    value = tris / dt / 1e6
+    sample = (f"{len(meshes)} meshes of the batch generator (every {max(1, count // take)}-th mesh, budgets scaled to {tris} triangles in total), built concurrently by the unmodified "
+              f"BuildClusterLODArtifactsFromGeometry (mesh mode): outer parallel-for over meshes on {min(len(meshes), cores)} threads, {dt:.2f} s per step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mtris/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic", "config": _batch_config(max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_scene_batch(args):
-    """CLODB200_BENCH_WORKLOAD=C4 (opt-in): a scene batch of independent meshes of the C4 generator (type = i mod 3, log-uniform
-    triangle budgets), sharded by mesh across the ranks (LPT, basicrenderer_b200/sharding.py); every rank builds its meshes one
-    after the other and the cache metadata blobs are gathered to all ranks. Total work is fixed as N grows (strong scaling).
-    CLODB200_BENCH_MESHES / CLODB200_BENCH_BATCH_TRIS bound the batch (default 48 meshes, 48 M triangles: the C4 mix at 1/20 scale)."""
+    """CLODB200_BENCH_WORKLOAD=C4 | C5 (opt-in): the scene batch configurations of BASELINE.json. C4: 512 independent meshes of the
+    scene generator (type = i mod 3 in {sphere, heightfield, torus}, log-uniform triangle budgets in [1e4, 2e6] rescaled to
+    1.0 B triangles in total); C5: 4 096 meshes, 8.0 B triangles. The meshes are sharded by mesh across the ranks (LPT,
+    basicrenderer_b200/sharding.py), every rank generates its shard on its GPU, keeps several builds in flight (one host thread
+    and build context each) and the batch ends with one NCCL gather of the cache metadata blobs. Total work is fixed as N grows
+    (strong scaling). CLODB200_BENCH_MESHES / CLODB200_BENCH_BATCH_TRIS override the batch size."""
     import torch
     import torch.distributed as dist
 
@@ -286,14 +340,16 @@ def run_scene_batch(args):
 
     lib = load(local)
     _comm_setup(lib, rank, world)
-    count = int(os.environ.get("CLODB200_BENCH_MESHES", 48))
-    total = float(os.environ.get("CLODB200_BENCH_BATCH_TRIS", 48e6))
+    count, total = _batch_shape()
     budgets = meshgen.scene_batch_sizes(count, total)
     mine = sharding.assign_meshes([int(b) for b in budgets], world)[rank]
-    meshes = [meshgen.scene_mesh(i, budgets[i]) for i in mine]
-    host = [(_pin(art.interleave(m.positions, m.normals)), _pin(m.indices)) for m in meshes]
+    meshes = [meshgen.scene_mesh_torch(i, budgets[i]) for i in mine]
+    torch.cuda.empty_cache()
+    pin = total <= 2.0e9  # the 8 B-triangle aggregate keeps its host copies pageable (24 GB per rank at N = 8)
+    host = [((_pin(m.vertices), _pin(m.indices)) if pin else (m.vertices, m.indices)) for m in meshes]
     handles = [lib.upload_geometry(v, i, art.VERTEX_NORMALS) for v, i in host]
     my_tris = sum(m.triangle_count for m in meshes)
+    del meshes
 
     def barrier():
         if world > 1:
@@ -302,17 +358,23 @@ def run_scene_batch(args):
 
     # several builds in flight per GPU: every worker thread owns a build context (stream, arenas) inside the library
     workers = max(1, int(os.environ.get("CLODB200_BENCH_THREADS", 4)))
-    lanes = sharding.assign_meshes([meshes[k].triangle_count for k in range(len(mine))], workers)
+    # largest meshes first, workers take the next mesh when they finish one (the way the reference's parallel-for hands out primitives)
+    order = sorted(range(len(mine)), key=lambda k: -int(host[k][1].size))
+    import queue
     from concurrent.futures import ThreadPoolExecutor
 
     pool = ThreadPoolExecutor(max_workers=workers)
 
     lane_launches = []
 
-    def build_lane(lane, resident):
+    def build_lane(todo, resident):
         out = []
         l0 = lib.launch_count  # per calling thread
-        for k in lane:
+        while True:
+            try:
+                k = todo.get_nowait()
+            except queue.Empty:
+                break
             rec = lib.build_artifacts_resident(handles[k], views=True, keep_handle=True) if resident else lib.build_artifacts(host[k][0], host[k][1], art.VERTEX_NORMALS, views=True, keep_handle=True)
             out.append((mine[k], lib.serialize_metadata(rec, f"clod_mesh{mine[k]}.clodbin", "bench", f"/mesh{mine[k]}")))
             lib.free_artifacts(rec)
@@ -320,7 +382,10 @@ def run_scene_batch(args):
         return out
 
     def step(resident):
-        done = [r for lane_out in pool.map(lambda lane: build_lane(lane, resident), lanes) for r in lane_out]
+        todo = queue.SimpleQueue()
+        for k in order:
+            todo.put(k)
+        done = [r for lane_out in pool.map(lambda _w: build_lane(todo, resident), range(workers)) for r in lane_out]
         done.sort()
         # one gather per batch, through the library's own NCCL all-gather (csrc/comm.cu)
         gathered = sharding.gather_metadata_end(lib, sharding.gather_metadata_begin(lib, [i for i, _ in done], [b for _, b in done]))
@@ -366,8 +431,9 @@ def run_scene_batch(args):
         print(json.dumps({
             "metric": "Mtris/s full cluster-LOD DAG build", "value": tris / (ms_per_step * 1e-3) / 1e6, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-            "config": {"workload": f"C4 shape: scene batch of {count} independent meshes ({int(tris)} triangles; sphere / heightfield / torus, log-uniform budgets {int(budgets.min())}..{int(budgets.max())}), "
-                                   f"sharded by mesh over {world} GPU(s) (LPT), {workers} builds in flight per GPU (one host thread + build context each), metadata blobs ({blob_bytes} B) gathered to every rank", "l2": "meshes are built back to back; each build streams its own arrays", "timing": "host clock between device-wide synchronisations (several streams), max over ranks"},
+            "config": _batch_config(world),
+            "output": {"meshes": count, "triangles": int(tris), "mesh_triangles_min": int(budgets.min()), "mesh_triangles_max": int(budgets.max()), "builds_in_flight_per_gpu": workers, "metadata_bytes_gathered": blob_bytes,
+                       "timing": "host clock between device-wide synchronisations (several build streams per GPU), max over ranks"},
             "clocks": _clock_summary(clock_samples),
             "e2e": {"value": tris / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": int(sum(v.nbytes + i.nbytes for v, i in host)), "d2h_bytes_per_step": None},
             "gpu_launches": int(launches),
@@ -384,7 +450,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    if WORKLOAD == "C4":
+    if WORKLOAD in ("C4", "C5"):
         return run_scene_batch(args)
     rank, world, local = _dist()
     if world > 1:
@@ -599,6 +665,8 @@ def run_reference(args):
     rank, world, _ = _dist()
     if rank != 0:
         return
+    if WORKLOAD in ("C4", "C5"):
+        return run_reference_batch(args)
     n_meshes = max(1, args.gpus)  # the workload of the N-GPU arm is N independent meshes
     meshes = [_reference_sample_mesh(index=i) for i in range(n_meshes)]
     cores = os.cpu_count() or 1
