@@ -1237,10 +1237,10 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 
 	// ---- a16, first half: bucket order (first-seen `refined`, stable) fixes the meshlet order of every group (CLU.cpp:905-984)
 	std::vector<u32> ordered(M); // position in group-bucket order -> emission index
-	{
+	host_parallel_for(G, 64, [&](size_t g_begin, size_t g_end, size_t) {
 		std::vector<int> bucket_refined;
 		std::vector<u32> bucket_count, bucket_of;
-		for (u32 g = 0; g < G; ++g)
+		for (u32 g = u32(g_begin); g < u32(g_end); ++g)
 		{
 			const GroupRec& gr = sink.groups[g];
 			bucket_refined.clear();
@@ -1270,7 +1270,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 			for (u32 j = 0; j < gr.count; ++j)
 				ordered[gr.first + bucket_count[bucket_of[j]]++] = gr.first + j;
 		}
-	}
+	});
 
 	LevelTable levels;
 	memset(&levels, 0, sizeof(levels));
@@ -1306,10 +1306,15 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	std::vector<MeshletJob> jobs(M);
 	std::vector<u32> group_of(M);
 	size_t vertex_refs = 0, triangle_total = 0;
-	for (u32 g = 0; g < G; ++g)
-		for (u32 j = 0; j < sink.groups[g].count; ++j)
-			group_of[sink.groups[g].first + j] = g;
-	for (u32 m = 0; m < M; ++m)
+	host_parallel_for(G, 64, [&](size_t g_begin, size_t g_end, size_t) {
+		for (u32 g = u32(g_begin); g < u32(g_end); ++g)
+			for (u32 j = 0; j < sink.groups[g].count; ++j)
+				group_of[sink.groups[g].first + j] = g;
+	});
+	std::vector<size_t> part_vertex_refs(host_parallel_chunks(M, 16384), 0), part_triangles(host_parallel_chunks(M, 16384), 0);
+	host_parallel_for(M, 16384, [&](size_t m_begin, size_t m_end, size_t chunk) {
+	size_t vertex_refs = 0, triangle_total = 0;
+	for (u32 m = u32(m_begin); m < u32(m_end); ++m)
 	{
 		const MeshletRec& r = sink.meshlets[ordered[m]];
 		MeshletJob& job = jobs[m];
@@ -1324,6 +1329,14 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		memcpy(job.bounds, r.bounds, sizeof(job.bounds));
 		vertex_refs += r.vertex_count;
 		triangle_total += r.tri_count;
+	}
+	part_vertex_refs[chunk] = vertex_refs;
+	part_triangles[chunk] = triangle_total;
+	});
+	for (size_t c = 0; c < part_vertex_refs.size(); ++c)
+	{
+		vertex_refs += part_vertex_refs[c];
+		triangle_total += part_triangles[c];
 	}
 
 	lap("bucket order + jobs (host)");
@@ -1356,7 +1369,8 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	// per-(meshlet, set) UV compression parameters (CLU.cpp:1268-1306)
 	std::vector<UvJob> uv_jobs(size_t(M) * U);
 	std::vector<u32> uv_bits_total(size_t(M) * U); // totalUvBits / vertex = bitsU + bitsV
-	for (size_t i = 0; i < size_t(M) * U; ++i)
+	host_parallel_for(size_t(M) * U, 32768, [&](size_t i_begin, size_t i_end, size_t) {
+	for (size_t i = i_begin; i < i_end; ++i)
 	{
 		const float* r = &uv_ranges[i * 4];
 		float min_u = r[0], min_v = r[1], max_u = r[2], max_v = r[3];
@@ -1370,6 +1384,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		uv_jobs[i].bits = (bits_u & 0xFFu) | ((bits_v & 0xFFu) << 8);
 		uv_bits_total[i] = bits_u + bits_v;
 	}
+	});
 	auto add_meshlet = [&](PageTotals& t, u32 m) {
 		t.meshlets++;
 		t.position_bytes += jobs[m].vertex_count * 12;
@@ -1380,20 +1395,25 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	};
 
 	// ---- a16, second half: greedy group pages, segments, segment spheres, group records (CLU.cpp:1348-1495)
-	std::vector<ClodGroup> groups(G);
-	std::vector<ClodChunk> chunks(G);
-	std::vector<ClodSegment> segments;
-	std::vector<u32> segment_first; // first meshlet (group-bucket order index) of each segment
-	std::vector<float> segment_bounds;
+	// Phase 1 (host threads, one group at a time each): everything that only depends on the group's own meshlets. Phase 2 (serial):
+	// the running totals (firstMeshlet, firstGroupVertex, firstSegment) and the concatenation in group order.
+	struct GroupLayout
 	{
-		u32 cumulative_meshlets = 0, cumulative_vertices = 0;
+		std::vector<ClodSegment> segs; // final order: terminal segments first (stable)
+		std::vector<u32> seg_first;
+		std::vector<float> seg_bounds;
+		u32 page_count = 0, terminal_segments = 0, tri_bytes = 0;
+	};
+	std::vector<GroupLayout> layouts(G);
+	host_parallel_for(G, 32, [&](size_t g_begin, size_t g_end, size_t) {
 		std::vector<u32> page_first;
 		std::vector<ClodSegment> gsegs;
 		std::vector<u32> gseg_first;
 		std::vector<u32> order;
-		for (u32 g = 0; g < G; ++g)
+		for (u32 g = u32(g_begin); g < u32(g_end); ++g)
 		{
 			const GroupRec& gr = sink.groups[g];
+			GroupLayout& lay = layouts[g];
 			page_first.assign(1, gr.first);
 			PageTotals cur;
 			for (u32 m = gr.first; m < gr.first + gr.count; ++m)
@@ -1431,7 +1451,45 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 			for (u32 i = 0; i < order.size(); ++i)
 				order[i] = i;
 			std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return (gsegs[a].refinedGroup < 0) > (gsegs[b].refinedGroup < 0); });
-
+			lay.page_count = u32(page_first.size() - 1);
+			for (u32 m = gr.first; m < gr.first + gr.count; ++m)
+				lay.tri_bytes += jobs[m].tri_count * 3;
+			bool leading = true;
+			lay.segs.reserve(order.size());
+			lay.seg_first.reserve(order.size());
+			lay.seg_bounds.reserve(order.size() * 4);
+			for (u32 i : order)
+			{
+				const ClodSegment& seg = gsegs[i];
+				if (seg.refinedGroup < 0 && leading)
+					lay.terminal_segments++;
+				else
+					leading = false;
+				lay.segs.push_back(seg);
+				lay.seg_first.push_back(gseg_first[i]);
+				float sphere[4];
+				sphere_bounds(sphere, jobs[gseg_first[i]].bounds, seg.meshletCount, sizeof(MeshletJob) / 4, jobs[gseg_first[i]].bounds + 3, sizeof(MeshletJob) / 4);
+				lay.seg_bounds.insert(lay.seg_bounds.end(), sphere, sphere + 4);
+			}
+		}
+	});
+	std::vector<ClodGroup> groups(G);
+	std::vector<ClodChunk> chunks(G);
+	std::vector<ClodSegment> segments;
+	std::vector<u32> segment_first; // first meshlet (group-bucket order index) of each segment
+	std::vector<float> segment_bounds;
+	{
+		size_t total_segments = 0;
+		for (u32 g = 0; g < G; ++g)
+			total_segments += layouts[g].segs.size();
+		segments.reserve(total_segments);
+		segment_first.reserve(total_segments);
+		segment_bounds.reserve(total_segments * 4);
+		u32 cumulative_meshlets = 0, cumulative_vertices = 0;
+		for (u32 g = 0; g < G; ++g)
+		{
+			const GroupRec& gr = sink.groups[g];
+			const GroupLayout& lay = layouts[g];
 			ClodGroup& out_group = groups[g];
 			memset(&out_group, 0, sizeof(out_group));
 			memcpy(out_group.bounds, gr.simplified, sizeof(out_group.bounds));
@@ -1441,40 +1499,54 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 			out_group.firstGroupVertex = cumulative_vertices;
 			out_group.groupVertexCount = group_vertices[g];
 			out_group.firstSegment = u32(segments.size());
-			out_group.segmentCount = u32(gsegs.size());
-			out_group.pageCount = u32(page_first.size() - 1);
+			out_group.segmentCount = u32(lay.segs.size());
+			out_group.terminalSegmentCount = lay.terminal_segments;
+			out_group.pageCount = lay.page_count;
 			out_group.parentGroupId = -1;
 			cumulative_meshlets += gr.count;
 			cumulative_vertices += group_vertices[g];
-			u32 tri_bytes = 0;
-			for (u32 m = gr.first; m < gr.first + gr.count; ++m)
-				tri_bytes += jobs[m].tri_count * 3;
-			chunks[g] = ClodChunk{group_vertices[g], gr.count, tri_bytes, 1u, has_normals ? 4u : 0u}; // CLOD_COMPRESSED_NORMALS = 1 << 2
-			bool leading = true;
-			for (u32 i : order)
-			{
-				const ClodSegment& seg = gsegs[i];
-				if (seg.refinedGroup < 0 && leading)
-					out_group.terminalSegmentCount++;
-				else
-					leading = false;
-				segments.push_back(seg);
-				segment_first.push_back(gseg_first[i]);
-				float sphere[4];
-				sphere_bounds(sphere, jobs[gseg_first[i]].bounds, seg.meshletCount, sizeof(MeshletJob) / 4, jobs[gseg_first[i]].bounds + 3, sizeof(MeshletJob) / 4);
-				segment_bounds.insert(segment_bounds.end(), sphere, sphere + 4);
-			}
+			chunks[g] = ClodChunk{group_vertices[g], gr.count, lay.tri_bytes, 1u, has_normals ? 4u : 0u}; // CLOD_COMPRESSED_NORMALS = 1 << 2
+			segments.insert(segments.end(), lay.segs.begin(), lay.segs.end());
+			segment_first.insert(segment_first.end(), lay.seg_first.begin(), lay.seg_first.end());
+			segment_bounds.insert(segment_bounds.end(), lay.seg_bounds.begin(), lay.seg_bounds.end());
 		}
 	}
+	layouts.clear();
+	lap("group pages + segments (host)");
 
 	// ---- a17
 	Hierarchy hier;
 	build_hierarchy(groups, segments, segment_bounds, hier);
 
+	lap("hierarchy (host)");
 	// ---- a18: mesh-wide greedy packing of segments, groups visited by (depth, parentGroupId, index) (CLU.cpp:2374-2470)
+	// The greedy fill is sequential in the reference and stays so here, but over per-segment totals (summed on host threads
+	// first; integer sums, so the order does not matter); the per-meshlet placement inside the finished pages runs on host
+	// threads afterwards, one page at a time each.
+	const u32 S = u32(segments.size());
+	std::vector<PageTotals> segment_totals(S);
+	host_parallel_for(S, 2048, [&](size_t s_begin, size_t s_end, size_t) {
+		for (u32 si = u32(s_begin); si < u32(s_end); ++si)
+		{
+			PageTotals t;
+			for (u32 k = 0; k < segments[si].meshletCount; ++k)
+				add_meshlet(t, segment_first[si] + k);
+			segment_totals[si] = t;
+		}
+	});
+	auto add_totals = [&](PageTotals& t, const PageTotals& o) {
+		t.meshlets += o.meshlets;
+		t.position_bytes += o.position_bytes;
+		t.vertex_count += o.vertex_count;
+		t.triangle_bytes += o.triangle_bytes;
+		for (u32 s = 0; s < U; ++s)
+			t.uv_bits[s] += o.uv_bits[s];
+	};
 	std::vector<PageRecord> pages;
 	std::vector<u64> page_offsets(1, 0);
 	std::vector<std::vector<u32>> group_pages(G);
+	std::vector<u32> page_segments;           // segment indices, page by page
+	std::vector<u32> page_segment_offsets(1, 0);
 	{
 		std::vector<u32> group_order(G);
 		for (u32 g = 0; g < G; ++g)
@@ -1486,10 +1558,10 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 				return groups[a].parentGroupId < groups[b].parentGroupId;
 			return a < b;
 		});
-		std::vector<u32> current; // segment indices of the page being filled
 		PageTotals cur;
+		size_t current_begin = 0; // page_segments[current_begin..) is the page being filled
 		auto flush = [&]() {
-			if (current.empty())
+			if (page_segments.size() == current_begin)
 				return;
 			PageRecord pr;
 			memset(&pr, 0, sizeof(pr));
@@ -1499,15 +1571,46 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 				throw Error("clodb200: a segment does not fit a 256 KiB page");
 			pr.base = page_offsets.back();
 			const u32 page_index = u32(pages.size());
+			for (size_t q = current_begin; q < page_segments.size(); ++q)
+				group_pages[jobs[segment_first[page_segments[q]]].group].push_back(page_index);
+			pages.push_back(pr);
+			page_offsets.push_back(pr.base + size);
+			page_segment_offsets.push_back(u32(page_segments.size()));
+			current_begin = page_segments.size();
+			cur = PageTotals();
+		};
+		for (u32 g : group_order)
+		{
+			const ClodGroup& group = groups[g];
+			for (u32 si = group.firstSegment; si < group.firstSegment + group.segmentCount; ++si)
+			{
+				const ClodSegment& seg = segments[si];
+				if (seg.meshletCount == 0)
+					continue;
+				PageTotals cand = cur;
+				add_totals(cand, segment_totals[si]);
+				if (page_blob_size(mask, U, cand) > kPageSize && page_segments.size() != current_begin)
+				{
+					flush();
+					cand = segment_totals[si];
+				}
+				page_segments.push_back(si);
+				cur = cand;
+			}
+		}
+		flush();
+	}
+	host_parallel_for(pages.size(), 8, [&](size_t p_begin, size_t p_end, size_t) {
+		for (u32 page_index = u32(p_begin); page_index < u32(p_end); ++page_index)
+		{
 			u32 slot = 0, pos_cursor = 0, attr_cursor = 0, tri_cursor = 0;
 			u64 uv_cursor[kMaxUvSets] = {};
-			for (u32 si : current)
+			for (u32 q = page_segment_offsets[page_index]; q < page_segment_offsets[page_index + 1]; ++q)
 			{
+				const u32 si = page_segments[q];
 				ClodSegment& seg = segments[si];
-				u32 owner = jobs[segment_first[si]].group;
 				seg.pageIndex = page_index;
 				seg.firstMeshletInPage = slot;
-				group_pages[owner].push_back(page_index);
 				for (u32 k = 0; k < seg.meshletCount; ++k)
 				{
 					u32 m = segment_first[si] + k;
@@ -1527,35 +1630,8 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 					}
 				}
 			}
-			pages.push_back(pr);
-			page_offsets.push_back(pr.base + size);
-			current.clear();
-			cur = PageTotals();
-		};
-		for (u32 g : group_order)
-		{
-			const ClodGroup& group = groups[g];
-			for (u32 si = group.firstSegment; si < group.firstSegment + group.segmentCount; ++si)
-			{
-				const ClodSegment& seg = segments[si];
-				if (seg.meshletCount == 0)
-					continue;
-				PageTotals cand = cur;
-				for (u32 k = 0; k < seg.meshletCount; ++k)
-					add_meshlet(cand, segment_first[si] + k);
-				if (page_blob_size(mask, U, cand) > kPageSize && !current.empty())
-				{
-					flush();
-					cand = PageTotals();
-					for (u32 k = 0; k < seg.meshletCount; ++k)
-						add_meshlet(cand, segment_first[si] + k);
-				}
-				current.push_back(si);
-				cur = cand;
-			}
 		}
-		flush();
-	}
+	});
 	const u32 page_count = u32(pages.size());
 	std::vector<u32> page_refs, page_ref_offsets;
 	for (u32 g = 0; g < G; ++g)
@@ -1576,7 +1652,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	}
 	page_ref_offsets.push_back(u32(page_refs.size()));
 
-	lap("pages/segments/hierarchy (host)");
+	lap("mesh page packing (host)");
 	// ---- page bytes on the device, one read-back
 	const size_t total_bytes = size_t(page_offsets.back());
 	u8* d_out = temp.alloc<u8>(total_bytes);

@@ -333,6 +333,19 @@ void scan_chain_reserve(size_t tiles)
 }
 #endif
 
+unsigned host_thread_limit()
+{
+	static unsigned limit = 0;
+	if (!limit)
+	{
+		unsigned hw = std::thread::hardware_concurrency();
+		limit = hw ? (hw < 16 ? hw : 16u) : 1u;
+		if (const char* e = getenv("CLODB200_HOST_THREADS"))
+			limit = unsigned(std::max(1, atoi(e)));
+	}
+	return limit;
+}
+
 void rt_thread_release() noexcept
 {
 #ifndef CLODB_EMU

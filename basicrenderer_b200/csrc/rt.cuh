@@ -11,8 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -330,6 +333,53 @@ struct ArenaScope
 		arena.release(m);
 	}
 };
+
+// Host-side parallel loop for the replay stages that run between kernels (per-group table building, page accounting): splits
+// [0, n) into contiguous chunks of at least `grain` items over up to 16 host threads; fn(begin, end, chunk_index) may only write
+// to disjoint outputs. Runs inline when the range is small. CLODB200_HOST_THREADS caps the thread count (1 = serial).
+unsigned host_thread_limit();
+template <typename F>
+static inline void host_parallel_for(size_t n, size_t grain, F&& fn)
+{
+	size_t chunks = grain ? n / grain : 1;
+	unsigned limit = host_thread_limit();
+	if (chunks > limit)
+		chunks = limit;
+	if (chunks <= 1)
+	{
+		if (n)
+			fn(size_t(0), n, size_t(0));
+		return;
+	}
+	std::vector<std::thread> threads;
+	std::exception_ptr error;
+	std::mutex error_mutex;
+	auto run = [&](size_t c) {
+		try
+		{
+			fn(n * c / chunks, n * (c + 1) / chunks, c);
+		}
+		catch (...)
+		{
+			std::lock_guard<std::mutex> lock(error_mutex);
+			if (!error)
+				error = std::current_exception();
+		}
+	};
+	for (size_t c = 1; c < chunks; ++c)
+		threads.emplace_back(run, c);
+	run(0);
+	for (std::thread& t : threads)
+		t.join();
+	if (error)
+		std::rethrow_exception(error);
+}
+static inline size_t host_parallel_chunks(size_t n, size_t grain)
+{
+	size_t chunks = grain ? n / grain : 1;
+	unsigned limit = host_thread_limit();
+	return chunks > limit ? limit : (chunks < 1 ? 1 : chunks);
+}
 
 template <typename T>
 static inline T dev_read(const T* p)

@@ -69,8 +69,26 @@ KERNEL_BYTES_PER_THREAD = {
     "(k_scan_chained<T, Op>)": 8 * 8,
     "(k_scan_chained<T, Op, SCAN_THREADS, SCAN_ITEMS>)": 8 * 8,
     "(k_scan_chained<T, Op, SCAN_LARGE_THREADS, SCAN_LARGE_ITEMS>)": 16 * 8,
-    # persistent kernels: no per-thread figure (work is data dependent); reported without a roofline fraction
+    # per candidate: sorted id 4 + status 1 + group 4 + error 4 + the three prefix arrays 4 + 4 + 8
+    "k_cut_find": 29,
+    "k_cut_inputs": 4 + 1 + 4 + 4 + 4 + 1 + 4 + 4 + 8,
+    "k_cut_apply": 4 + 1 + 4 + 4,
+    # listing pass: status 1 + sorted id 4 + group 4 per candidate (the gathers and the record only for listed candidates)
+    "k_wave_list": 9,
+    "k_pick_flags": 4 + 4 + 4 + 4 + 2 + 4,
+    "k_pick_emit": 4 + 4 + 4,
+    "k_adj_count": 4 + 4,
+    "k_adj_fill": 4 + 4 + 4 + 4,
+}
 
+# Kernels without a byte model are not bandwidth kernels; what bounds them, from the ncu captures in profiles/r02_ncu_kernels.md
+KERNEL_LIMITER = {
+    "k_update_quadrics": "latency: one thread per candidate, the ~8 % that were performed run a chain of dependent scattered read-modify-writes of 44..156-byte quadrics (long_scoreboard 520 warps per issue)",
+    "k_merge_rounds": "latency + grid barriers: persistent cooperative kernel, 6 barriers per merge round over a shrinking edge list (barrier 55 warps per issue)",
+    "k_build_clusters_warp": "compute: meshlet assembly + optimizeMeshlet per warp, SM throughput 88 %",
+    "k_cluster_bounds_warp": "compute: 7-axis extremal search + sequential sphere growth per cluster",
+    "k_leaf_test_warp": "latency: one warp per tree node, small launches",
+    "k_resolve_nodes": "launch latency: a few thousand nodes per launch",
 }
 
 
@@ -106,6 +124,8 @@ def _kernel_table(rows, peak_gbs, limit=10):
             gbs = bpt * threads / (ms * 1e-3) / 1e9
             entry["algorithmic_gbs"] = round(gbs, 1)
             entry["frac"] = round(gbs / peak_gbs, 4)
+        elif name in KERNEL_LIMITER:
+            entry["limiter"] = KERNEL_LIMITER[name]
         out.append(entry)
     return out
 
