@@ -892,6 +892,42 @@ struct ArtifactSink : DagSink
 	{
 		level_tri.push_back(level.tri);
 	}
+	bool emit_level_bulk(const LevelBulk& b, std::vector<int>& group_ids) override
+	{
+		const u32 level = u32(level_tri.size() - 1);
+		const size_t base_group = groups.size(), base_meshlet = meshlets.size();
+		groups.resize(base_group + b.group_count);
+		meshlets.resize(base_meshlet + b.cluster_count);
+		host_parallel_for(b.group_count, 16, [&](size_t g_begin, size_t g_end, size_t) {
+			for (size_t g = g_begin; g < g_end; ++g)
+			{
+				const u32 first = b.group_cluster_offset[g], last = b.group_cluster_offset[g + 1];
+				GroupRec& gr = groups[base_group + g];
+				gr.depth = b.depth;
+				memcpy(gr.simplified, b.group_bounds5 + g * 5, sizeof(gr.simplified));
+				gr.first = u32(base_meshlet + first);
+				gr.count = last - first;
+				for (u32 j = first; j < last; ++j)
+				{
+					const u32 c = b.group_clusters[j];
+					MeshletRec& m = meshlets[base_meshlet + j];
+					m.level = level;
+					m.tri_begin = b.cluster_tri_offset[c];
+					m.tri_count = b.cluster_tri_offset[c + 1] - b.cluster_tri_offset[c];
+					m.vertex_count = b.cluster_vertex_count[c];
+					m.refined = b.refined[c];
+					const bool precise = b.use_precise && b.refined[c] != -1;
+					const float* src = precise ? b.precise4 + size_t(c) * 4 : b.bounds5 + size_t(c) * 5;
+					m.bounds[0] = src[0];
+					m.bounds[1] = src[1];
+					m.bounds[2] = src[2];
+					m.bounds[3] = src[3];
+				}
+				group_ids[g] = int(base_group + g); // CaptureOutputContext::nextGroupId, CLU.cpp:5498
+			}
+		});
+		return true;
+	}
 	int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t) override
 	{
 		GroupRec g;

@@ -104,6 +104,27 @@ static size_t emit_level(const ClusterSet& cs, const LevelHost& host, const std:
 	sink.begin_level(cs, depth);
 	sink.level_cluster_tri_offset = off;
 	group_ids.assign(groups.group_count, -1);
+	if (!tri)
+	{
+		LevelBulk bulk;
+		bulk.depth = depth;
+		bulk.cluster_count = cs.cluster_count;
+		bulk.group_count = groups.group_count;
+		bulk.group_cluster_offset = groups.group_cluster_offset_host.data();
+		bulk.group_clusters = group_clusters.data();
+		bulk.refined = refined.data();
+		bulk.bounds5 = bounds5.data();
+		bulk.precise4 = precise4.data();
+		bulk.use_precise = config.optimize_bounds;
+		bulk.group_bounds5 = group_bounds5.data();
+		bulk.cluster_tri_offset = off;
+		bulk.cluster_vertex_count = vcount;
+		if (sink.emit_level_bulk(bulk, group_ids))
+		{
+			stats.groups += groups.group_count;
+			return cs.cluster_count;
+		}
+	}
 	for (u32 g = 0; g < groups.group_count; ++g)
 	{
 		u32 b = groups.group_cluster_offset_host[g], e = groups.group_cluster_offset_host[g + 1];

@@ -23,9 +23,32 @@ struct DagGroup
 	float simplified[5];
 };
 
+// One whole DAG level for sinks that can take it at once (host arrays; cluster ids are level-local).
+struct LevelBulk
+{
+	int depth;
+	u32 cluster_count, group_count;
+	const u32* group_cluster_offset; // group_count + 1
+	const u32* group_clusters;       // cluster ids, group-major (callback order)
+	const int* refined;              // per cluster
+	const float* bounds5;            // per cluster: inherited sphere + error
+	const float* precise4;           // per cluster: sphere of the cluster's own geometry
+	bool use_precise;                // clusterlod.h:689 (optimize_bounds): precise sphere for clusters with refined != -1
+	const float* group_bounds5;      // per group: simplified sphere + error (after the error rule)
+	const u32* cluster_tri_offset;   // cluster_count + 1
+	const u32* cluster_vertex_count; // per cluster
+};
+
 struct DagSink
 {
 	virtual ~DagSink() {}
+	// Optional fast path: take the whole level in one call (the sink may use host threads) and return true after filling
+	// group_ids[g] with what group() would have returned for group g, in order. Sinks that forward to a user callback keep the
+	// serial per-group contract (clusterlod.h:895-926) and leave this alone.
+	virtual bool emit_level_bulk(const LevelBulk& /*level*/, std::vector<int>& /*group_ids*/)
+	{
+		return false;
+	}
 	// returns the id stored as `refined` for clusters produced from this group
 	virtual int group(const DagGroup& group, const DagCluster* clusters, size_t cluster_count, size_t task_index) = 0;
 	// false: the level's index lists stay on the device (DagCluster::indices is null); the sink reads them from the
