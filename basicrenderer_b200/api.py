@@ -407,18 +407,18 @@ class ClodLib:
             self._lib.clodb200_artifactsFree(handle)
         return a
 
-    def build_artifacts(self, vertices, indices, flags, uv_sets=None, tangents=None, settings=None, views: bool = False, keep_handle: bool = False):
+    def build_artifacts(self, vertices, indices, flags, uv_sets=None, tangents=None, settings=None, views: bool = False, keep_handle: bool = False, skinning=None):
         """Host arrays in, ClusterLODPrebuildArtifacts out (upload + DAG build + page encode + read-back)."""
         from . import artifacts as _art
 
-        g, keep = _art.make_geometry(vertices, indices, flags, uv_sets, tangents)
+        g, keep = _art.make_geometry(vertices, indices, flags, uv_sets, tangents, skinning)
         st = settings or self.default_builder_settings()
         return self._artifacts(self._lib.clodb200_buildArtifacts(C.byref(g), C.byref(st)), views=views, keep_handle=keep_handle)
 
-    def upload_geometry(self, vertices, indices, flags, uv_sets=None, tangents=None, settings=None):
+    def upload_geometry(self, vertices, indices, flags, uv_sets=None, tangents=None, settings=None, skinning=None):
         from . import artifacts as _art
 
-        g, keep = _art.make_geometry(vertices, indices, flags, uv_sets, tangents)
+        g, keep = _art.make_geometry(vertices, indices, flags, uv_sets, tangents, skinning)
         st = settings or self.default_builder_settings()
         h = self._lib.clodb200_geometryUpload(C.byref(g), C.byref(st))
         if not h:

@@ -56,7 +56,8 @@ class UvSet(C.Structure):
 
 class Geometry(C.Structure):
     _fields_ = [("vertices", C.c_void_p), ("vertex_count", C.c_size_t), ("vertex_stride", C.c_uint), ("vertex_flags", C.c_uint),
-                ("indices", C.c_void_p), ("index_count", C.c_size_t), ("uv_sets", C.POINTER(UvSet)), ("uv_set_count", C.c_size_t), ("tangents", C.c_void_p)]
+                ("indices", C.c_void_p), ("index_count", C.c_size_t), ("uv_sets", C.POINTER(UvSet)), ("uv_set_count", C.c_size_t), ("tangents", C.c_void_p),
+                ("skinning_vertices", C.c_void_p), ("skinning_vertex_bytes", C.c_size_t), ("skinning_vertex_stride", C.c_uint)]
 
 
 class Artifacts:
@@ -109,8 +110,20 @@ def bind(lib) -> None:
     L.clodb200_artifactsSerializeMetadata.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t]
 
 
-def make_geometry(vertices, indices, flags, uv_sets=None, tangents=None):
-    """-> (Geometry, keep-alive list). vertices: float32 [V, stride/4] interleaved; uv_sets: list of float32 [V, 2]."""
+def skinning_stream(positions, normals, joints, weights) -> np.ndarray:
+    """The importer's skinning vertex stream as bytes [V, 88]: position f32x3, normal f32x3, joints u32x8, weights f32x8."""
+    V = positions.shape[0]
+    out = np.zeros((V, 88), np.uint8)
+    out[:, 0:12] = np.ascontiguousarray(positions, np.float32).view(np.uint8).reshape(V, 12)
+    out[:, 12:24] = np.ascontiguousarray(normals, np.float32).view(np.uint8).reshape(V, 12)
+    out[:, 24:56] = np.ascontiguousarray(joints, np.uint32).view(np.uint8).reshape(V, 32)
+    out[:, 56:88] = np.ascontiguousarray(weights, np.float32).view(np.uint8).reshape(V, 32)
+    return out
+
+
+def make_geometry(vertices, indices, flags, uv_sets=None, tangents=None, skinning=None):
+    """-> (Geometry, keep-alive list). vertices: float32 [V, stride/4] interleaved; uv_sets: list of float32 [V, 2];
+    skinning: uint8 [V', stride] skinning vertex stream (skinning_stream())."""
     vertices = np.ascontiguousarray(vertices, np.float32)
     indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
     keep = [vertices, indices]
@@ -135,6 +148,12 @@ def make_geometry(vertices, indices, flags, uv_sets=None, tangents=None):
         tangents = np.ascontiguousarray(tangents, np.float32)
         keep.append(tangents)
         g.tangents = tangents.ctypes.data
+    if skinning is not None:
+        skinning = np.ascontiguousarray(skinning, np.uint8)
+        keep.append(skinning)
+        g.skinning_vertices = skinning.ctypes.data
+        g.skinning_vertex_bytes = skinning.size
+        g.skinning_vertex_stride = skinning.shape[1]
     return g, keep
 
 

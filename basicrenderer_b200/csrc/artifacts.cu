@@ -61,7 +61,9 @@ static_assert(sizeof(ClodGroup) == 76 && sizeof(ClodSegment) == 16 && sizeof(Clo
 
 static const u32 kPageSize = 256u * 1024u; // CLOD_PAGE_SIZE, shaders/Common/defines.h
 static const u32 kPageHeaderSize = 64, kDescriptorSize = 64, kUvDescriptorSize = 32;
-static const u32 kAttrNormal = 1u << 0, kAttrColor = 1u << 3; // CLOD_PAGE_ATTRIBUTE_*, ClusterLODShaderTypes.h:15-18
+static const u32 kAttrNormal = 1u << 0, kAttrJoints = 1u << 1, kAttrWeights = 1u << 2, kAttrColor = 1u << 3; // CLOD_PAGE_ATTRIBUTE_*, ClusterLODShaderTypes.h:15-18
+static const u32 kSkinJointOffset = 24, kSkinInfluenceBytes = 64; // skinning vertex: pos f3, normal f3, then PackedSkinningInfluences (CLU.cpp:50-56, :1100)
+static const u32 kMaxSkinInfluences = 8;
 static const u32 kMaxLevels = 48;
 
 // ---- device side --------------------------------------------------------------------------------------------------------
@@ -78,8 +80,12 @@ struct MeshletJob
 	u32 tri_word;  // triangleCount:16 | refinedGroup+1:16 (CLU.cpp:1631-1635)
 	u32 page;      // mesh page index
 	u32 slot;      // meshlet index inside the page
-	u32 pos_cursor, attr_cursor, tri_cursor, pad;
+	u32 pos_cursor, attr_cursor, tri_cursor;
+	u32 bone_cursor;  // first entry of the meshlet's bone list in the page's bone-index stream (descriptor boneListOffset)
 	float bounds[4];
+	u32 bone_count;   // distinct joints with a positive weight among the meshlet's vertices (descriptor boneCount)
+	u32 bone_scratch; // where the pre-pass left the sorted list (u32 index into the scratch array)
+	u32 pad[2];
 };
 
 struct PageRecord
@@ -105,7 +111,66 @@ struct VertexStreams
 	u32 uv_set_count;
 	const float* uv_values[kMaxUvSets];
 	u32 uv_stride[kMaxUvSets];
+	// skinned meshes (CLU.cpp:1091-1120): a second vertex stream that carries two uint4 joints and two float4 weights per vertex
+	const u8* skinning; // null = no skinning stream
+	u32 skinning_stride;
+	u32 skinning_count; // vertices beyond this read as zero influences (:1107-1110)
 };
+
+// The meshlet's bone list (CLU.cpp:1240-1265): joints that carry a positive weight on any of its vertices, sorted ascending, unique.
+// Built by insertion into `list` (room for 8 entries per vertex); returns the count. One thread per meshlet: skinned meshes are
+// character-sized and the lists are a few dozen entries.
+DEVFN u32 meshlet_bone_list(const VertexStreams& vs, const u32* vertices, u32 count, u32* list)
+{
+	u32 n = 0;
+	for (u32 vi = 0; vi < count; ++vi)
+	{
+		if (vertices[vi] >= vs.skinning_count)
+			continue;
+		const u8* sv = vs.skinning + size_t(vertices[vi]) * vs.skinning_stride + kSkinJointOffset;
+		const u32* joints = reinterpret_cast<const u32*>(sv);
+		const float* weights = reinterpret_cast<const float*>(sv + 32);
+		for (u32 k = 0; k < kMaxSkinInfluences; ++k)
+		{
+			if (!(weights[k] > 0.0f))
+				continue;
+			u32 j = joints[k];
+			u32 lo = 0, hi = n;
+			while (lo < hi)
+			{
+				u32 mid = (lo + hi) / 2;
+				if (list[mid] < j)
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			if (lo < n && list[lo] == j)
+				continue;
+			for (u32 q = n; q > lo; --q)
+				list[q] = list[q - 1];
+			list[lo] = j;
+			++n;
+		}
+	}
+	return n;
+}
+
+// joints (two uint4) and weights (two float4) of one meshlet vertex into the page arrays; vertices without a skinning record get zeros
+DEVFN void write_skinning(const VertexStreams& vs, u32 vertex, u32* joints_out, u32* weights_out)
+{
+	if (vertex < vs.skinning_count)
+	{
+		const u32* src = reinterpret_cast<const u32*>(vs.skinning + size_t(vertex) * vs.skinning_stride + kSkinJointOffset);
+		for (int k = 0; k < 8; ++k)
+		{
+			joints_out[k] = src[k];
+			weights_out[k] = src[8 + k];
+		}
+	}
+	else
+		for (int k = 0; k < 8; ++k)
+			joints_out[k] = weights_out[k] = 0;
+}
 
 KERNEL k_split_vertex_streams(const u8* __restrict__ vertices, u32 stride, size_t V, float* positions3, float* attributes, u32 astride, u32 with_normals, const float* __restrict__ tangents4)
 {
@@ -276,7 +341,8 @@ DEVFN u32 local_table_build(LocalTable& t, const u32* idx, u32 n, u8* local_ids)
 	return t.count;
 }
 
-KERNEL k_meshlet_prepass(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, u64* table, u64 table_mask, u32* group_vertex_count, float* uv_ranges, u32* errors)
+KERNEL k_meshlet_prepass(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, u64* table, u64 table_mask, u32* group_vertex_count, float* uv_ranges, u32* errors,
+    u32* bone_scratch, u32* bone_counts)
 {
 	size_t m = GTID;
 	if (m >= M)
@@ -295,6 +361,8 @@ KERNEL k_meshlet_prepass(const MeshletJob* __restrict__ jobs, u32 M, LevelTable 
 		inserted += group_vertex_insert(table, table_mask, job.group, t.vertices[vi]) ? 1u : 0u;
 	if (inserted)
 		atomicAdd(&group_vertex_count[job.group], inserted);
+	if (vs.skinning)
+		bone_counts[m] = meshlet_bone_list(vs, t.vertices, count, bone_scratch + job.bone_scratch);
 	for (u32 s = 0; s < vs.uv_set_count; ++s)
 	{
 		float mn_u = FLT_MAX, mn_v = FLT_MAX, mx_u = -FLT_MAX, mx_v = -FLT_MAX;
@@ -317,11 +385,11 @@ DEVFN void write_descriptor(u32* desc, const MeshletJob& job)
 	desc[0] = job.pos_cursor;
 	desc[1] = job.attr_cursor;
 	desc[2] = job.tri_cursor;
-	desc[3] = 0; // boneListOffset
+	desc[3] = job.bone_cursor; // boneListOffset
 	desc[4] = desc[5] = desc[6] = 0;
 	desc[7] = (job.vertex_count & 0xFFu) << 24;
 	desc[8] = job.tri_word;
-	desc[9] = 0; // boneCount
+	desc[9] = job.bone_count;
 	desc[10] = job.group;
 	desc[11] = 0;
 	desc[12] = __float_as_uint(job.bounds[0]);
@@ -330,7 +398,8 @@ DEVFN void write_descriptor(u32* desc, const MeshletJob& job)
 	desc[15] = __float_as_uint(job.bounds[3]);
 }
 
-KERNEL k_write_pages(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, const PageRecord* __restrict__ pages, const UvJob* __restrict__ uv_jobs, u8* out, u32* errors)
+KERNEL k_write_pages(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, const PageRecord* __restrict__ pages, const UvJob* __restrict__ uv_jobs, u8* out, u32* errors,
+    const u32* __restrict__ bone_scratch)
 {
 	size_t m = GTID;
 	if (m >= M)
@@ -377,7 +446,11 @@ KERNEL k_write_pages(const MeshletJob* __restrict__ jobs, u32 M, LevelTable leve
 			const float* c = reinterpret_cast<const float*>(v + vs.color_offset);
 			col[vi] = pack_color(c[0], c[1], c[2]);
 		}
+		if (hdr[9])
+			write_skinning(vs, t.vertices[vi], reinterpret_cast<u32*>(page + hdr[9]) + size_t(job.attr_cursor + vi) * 8, reinterpret_cast<u32*>(page + hdr[10]) + size_t(job.attr_cursor + vi) * 8);
 	}
+	for (u32 b = 0; b < job.bone_count; ++b)
+		reinterpret_cast<u32*>(page + hdr[13])[job.bone_cursor + b] = bone_scratch[job.bone_scratch + b];
 	for (u32 s = 0; s < vs.uv_set_count; ++s)
 	{
 		UvJob uj = uv_jobs[m * vs.uv_set_count + s];
@@ -465,7 +538,8 @@ DEVFN u32 warp_table_build(WarpTable& t, const u32* __restrict__ idx, u32 n, int
 	return count;
 }
 
-static __global__ void __launch_bounds__(MW_WARPS * 32) k_meshlet_prepass_warp(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, u64* table, u64 table_mask, u32* group_vertex_count, float* uv_ranges, u32* errors)
+static __global__ void __launch_bounds__(MW_WARPS * 32) k_meshlet_prepass_warp(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, u64* table, u64 table_mask, u32* group_vertex_count, float* uv_ranges, u32* errors,
+    u32* bone_scratch, u32* bone_counts)
 {
 	__shared__ WarpTable s_tables[MW_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -498,6 +572,8 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_meshlet_prepass_warp(c
 		inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
 	if (lane == 0 && inserted)
 		atomicAdd(&group_vertex_count[job.group], inserted);
+	if (vs.skinning && lane == 0)
+		bone_counts[m] = meshlet_bone_list(vs, t.vertices, count, bone_scratch + job.bone_scratch);
 	for (u32 s = 0; s < vs.uv_set_count; ++s)
 	{
 		float mn_u = FLT_MAX, mn_v = FLT_MAX, mx_u = -FLT_MAX, mx_v = -FLT_MAX;
@@ -524,7 +600,8 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_meshlet_prepass_warp(c
 	}
 }
 
-static __global__ void __launch_bounds__(MW_WARPS * 32) k_write_pages_warp(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, const PageRecord* __restrict__ pages, const UvJob* __restrict__ uv_jobs, u8* out, u32* errors)
+static __global__ void __launch_bounds__(MW_WARPS * 32) k_write_pages_warp(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, const PageRecord* __restrict__ pages, const UvJob* __restrict__ uv_jobs, u8* out, u32* errors,
+    const u32* __restrict__ bone_scratch)
 {
 	__shared__ WarpTable s_tables[MW_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,6 +628,7 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_write_pages_warp(const
 	const PageRecord& pr = pages[job.page];
 	u8* page = out + pr.base;
 	u32 hdr_desc = pr.header[4], hdr_uvdesc = pr.header[5], hdr_pos = pr.header[6], hdr_nrm = pr.header[7], hdr_col = pr.header[8], hdr_uvdir = pr.header[11], hdr_tri = pr.header[12];
+	const u32 hdr_joints = pr.header[9], hdr_weights = pr.header[10], hdr_bones = pr.header[13];
 
 	// triangle bytes: corner k * 32 + lane -> local id; consecutive lanes write consecutive bytes
 	u8* tri_out = page + hdr_tri + job.tri_cursor;
@@ -592,7 +670,11 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_write_pages_warp(const
 			const float* c = reinterpret_cast<const float*>(v + vs.color_offset);
 			col[vi] = pack_color(__ldg(c), __ldg(c + 1), __ldg(c + 2));
 		}
+		if (hdr_joints)
+			write_skinning(vs, t.vertices[vi], reinterpret_cast<u32*>(page + hdr_joints) + size_t(job.attr_cursor + vi) * 8, reinterpret_cast<u32*>(page + hdr_weights) + size_t(job.attr_cursor + vi) * 8);
 	}
+	for (u32 b = lane; b < job.bone_count; b += 32)
+		reinterpret_cast<u32*>(page + hdr_bones)[job.bone_cursor + b] = bone_scratch[job.bone_scratch + b];
 	for (u32 s = 0; s < vs.uv_set_count; ++s)
 	{
 		UvJob uj = uv_jobs[size_t(m) * vs.uv_set_count + s];
@@ -641,11 +723,11 @@ u32 bits_needed_for_range(u32 range) // BitsNeededForRange, CLU.cpp:58-65
 
 struct PageTotals // PageTotals / TriangleMeshPageBuildTotals, CLU.cpp:1338-1346, 1883-1893
 {
-	u32 meshlets = 0, position_bytes = 0, vertex_count = 0, triangle_bytes = 0;
+	u32 meshlets = 0, position_bytes = 0, vertex_count = 0, triangle_bytes = 0, bone_indices = 0;
 	u64 uv_bits[kMaxUvSets] = {};
 };
 
-// ComputePageBlobSize, CLU.cpp:368-417 (no skinning streams, no bone lists on this path)
+// ComputePageBlobSize, CLU.cpp:368-417
 size_t page_blob_size(u32 mask, u32 uv_set_count, const PageTotals& t)
 {
 	size_t size = kPageHeaderSize;
@@ -657,13 +739,17 @@ size_t page_blob_size(u32 mask, u32 uv_set_count, const PageTotals& t)
 		size = align4(size) + align4(size_t(t.vertex_count) * 4);
 	if (mask & kAttrColor)
 		size = align4(size) + align4(size_t(t.vertex_count) * 4);
+	if (mask & kAttrJoints)
+		size = align4(size) + align4(size_t(t.vertex_count) * 32);
+	if (mask & kAttrWeights)
+		size = align4(size) + align4(size_t(t.vertex_count) * 32);
 	if (uv_set_count > 0)
 	{
 		size = align4(size) + align4(size_t(uv_set_count) * 4);
 		for (u32 s = 0; s < uv_set_count; ++s)
 			size = align4(size) + align4(size_t((t.uv_bits[s] + 31ull) / 32ull) * 4);
 	}
-	size = align4(size) + align4(0); // bone index stream
+	size = align4(size) + align4(size_t(t.bone_indices) * 4); // bone index stream
 	size = align4(size) + align4(size_t(t.triangle_bytes));
 	return align4(size);
 }
@@ -682,7 +768,13 @@ void page_layout(u32 mask, u32 uv_set_count, const PageTotals& t, PageRecord& pr
 	const size_t normal_bytes = has_normals ? size_t(t.vertex_count) * 4 : 0u;
 	const u32 color_offset = has_colors ? u32(align4(has_normals ? (normal_offset + normal_bytes) : (position_offset + position_bytes))) : 0u;
 	const size_t color_bytes = has_colors ? size_t(t.vertex_count) * 4 : 0u;
-	const size_t streams_end = has_colors ? (color_offset + color_bytes) : (has_normals ? (normal_offset + normal_bytes) : (position_offset + position_bytes));
+	const bool has_joints = (mask & kAttrJoints) != 0, has_weights = (mask & kAttrWeights) != 0;
+	const size_t attributes_end = has_colors ? (color_offset + color_bytes) : (has_normals ? (normal_offset + normal_bytes) : (position_offset + position_bytes));
+	const u32 joint_offset = has_joints ? u32(align4(attributes_end)) : 0u;
+	const size_t joint_bytes = has_joints ? size_t(t.vertex_count) * 32 : 0u;
+	const u32 weight_offset = has_weights ? u32(align4(has_joints ? (joint_offset + joint_bytes) : attributes_end)) : 0u;
+	const size_t weight_bytes = has_weights ? size_t(t.vertex_count) * 32 : 0u;
+	const size_t streams_end = has_weights ? (weight_offset + weight_bytes) : (has_joints ? (joint_offset + joint_bytes) : attributes_end);
 	const u32 uv_directory_offset = has_uv ? u32(align4(streams_end)) : 0u;
 	size_t uv_cursor = has_uv ? align4(size_t(uv_directory_offset) + size_t(uv_set_count) * 4) : align4(streams_end);
 	for (u32 s = 0; s < uv_set_count; ++s)
@@ -691,7 +783,7 @@ void page_layout(u32 mask, u32 uv_set_count, const PageTotals& t, PageRecord& pr
 		uv_cursor = align4(uv_cursor + size_t((t.uv_bits[s] + 31ull) / 32ull) * 4);
 	}
 	const u32 bone_offset = u32(align4(uv_cursor));
-	const u32 triangle_offset = u32(align4(bone_offset + 0));
+	const u32 triangle_offset = u32(align4(bone_offset + size_t(t.bone_indices) * 4));
 	total_size = u32(align4(triangle_offset + t.triangle_bytes));
 	u32* h = pr.header; // CLodPageHeader, ClusterLODShaderTypes.h:26-45
 	memset(h, 0, 64);
@@ -704,8 +796,8 @@ void page_layout(u32 mask, u32 uv_set_count, const PageTotals& t, PageRecord& pr
 	h[6] = position_offset;
 	h[7] = normal_offset;
 	h[8] = color_offset;
-	h[9] = 0;
-	h[10] = 0;
+	h[9] = joint_offset;
+	h[10] = weight_offset;
 	h[11] = uv_directory_offset;
 	h[12] = triangle_offset;
 	h[13] = bone_offset;
@@ -1333,7 +1425,15 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		vs.uv_stride[0] = stride / 4;
 	}
 	const u32 U = vs.uv_set_count;
-	const u32 mask = (has_normals ? kAttrNormal : 0u) | (has_colors ? kAttrColor : 0u);
+	// hasSkinningStream, CLU.cpp:1092-1097
+	const bool has_skinning = geo.skinning_vertices != nullptr && geo.skinning_stride >= kSkinJointOffset + kSkinInfluenceBytes && geo.skinning_vertex_count > 0;
+	if (has_skinning)
+	{
+		vs.skinning = geo.skinning_vertices;
+		vs.skinning_stride = geo.skinning_stride;
+		vs.skinning_count = u32(std::min<size_t>(geo.skinning_vertex_count, 0xffffffffu));
+	}
+	const u32 mask = (has_normals ? kAttrNormal : 0u) | (has_colors ? kAttrColor : 0u) | (has_skinning ? (kAttrJoints | kAttrWeights) : 0u);
 
 	Arena& temp = ws.temp;
 	ArenaScope scope(temp);
@@ -1375,6 +1475,23 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		triangle_total += part_triangles[c];
 	}
 
+	// skinned meshes: room for every meshlet's bone list (at most 8 joints per vertex) behind a prefix of the vertex counts
+	u32* d_bone_scratch = nullptr;
+	u32* d_bone_counts = nullptr;
+	if (has_skinning)
+	{
+		u64 cursor = 0;
+		for (u32 m = 0; m < M; ++m)
+		{
+			jobs[m].bone_scratch = u32(cursor);
+			cursor += u64(jobs[m].vertex_count) * kMaxSkinInfluences;
+		}
+		if (cursor > 0xffffffffull)
+			throw Error("clodb200: skinned mesh too large for the bone-list scratch (more than 2^32 influence slots)");
+		d_bone_scratch = temp.alloc<u32>(size_t(cursor) + 1);
+		d_bone_counts = temp.alloc<u32>(M);
+		dev_memset(d_bone_counts, 0, size_t(M) * 4);
+	}
 	lap("bucket order + jobs (host)");
 	// ---- device pre-pass: distinct vertices per group, UV ranges per meshlet
 	MeshletJob* d_jobs = temp.alloc<MeshletJob>(M);
@@ -1390,9 +1507,9 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	dev_memset(d_group_vertices, 0, size_t(G) * 4);
 	dev_memset(d_errors, 0, 16);
 #ifdef CLODB_EMU
-	LAUNCH(k_meshlet_prepass, M, d_jobs, M, levels, vs, d_table, table_size - 1, d_group_vertices, d_uv_ranges, d_errors);
+	LAUNCH(k_meshlet_prepass, M, d_jobs, M, levels, vs, d_table, table_size - 1, d_group_vertices, d_uv_ranges, d_errors, d_bone_scratch, d_bone_counts);
 #else
-	LAUNCH_GRID(k_meshlet_prepass_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_table, table_size - 1, d_group_vertices, d_uv_ranges, d_errors);
+	LAUNCH_GRID(k_meshlet_prepass_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_table, table_size - 1, d_group_vertices, d_uv_ranges, d_errors, d_bone_scratch, d_bone_counts);
 #endif
 	if (dev_read(d_errors))
 		throw Error("clodb200: meshlet vertex table does not match the cluster's vertex count");
@@ -1400,6 +1517,12 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	std::vector<float> uv_ranges;
 	if (U)
 		uv_ranges = dev_download(d_uv_ranges, size_t(M) * U * 4);
+	if (has_skinning)
+	{
+		std::vector<u32> bone_counts = dev_download(d_bone_counts, M);
+		for (u32 m = 0; m < M; ++m)
+			jobs[m].bone_count = bone_counts[m];
+	}
 
 	lap("meshlet pre-pass + read-back");
 	// per-(meshlet, set) UV compression parameters (CLU.cpp:1268-1306)
@@ -1426,6 +1549,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		t.position_bytes += jobs[m].vertex_count * 12;
 		t.vertex_count += jobs[m].vertex_count;
 		t.triangle_bytes += jobs[m].tri_count * 3;
+		t.bone_indices += jobs[m].bone_count;
 		for (u32 s = 0; s < U; ++s)
 			t.uv_bits[s] += u64(jobs[m].vertex_count) * uv_bits_total[size_t(m) * U + s];
 	};
@@ -1575,6 +1699,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 		t.position_bytes += o.position_bytes;
 		t.vertex_count += o.vertex_count;
 		t.triangle_bytes += o.triangle_bytes;
+		t.bone_indices += o.bone_indices;
 		for (u32 s = 0; s < U; ++s)
 			t.uv_bits[s] += o.uv_bits[s];
 	};
@@ -1639,7 +1764,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	host_parallel_for(pages.size(), 8, [&](size_t p_begin, size_t p_end, size_t) {
 		for (u32 page_index = u32(p_begin); page_index < u32(p_end); ++page_index)
 		{
-			u32 slot = 0, pos_cursor = 0, attr_cursor = 0, tri_cursor = 0;
+			u32 slot = 0, pos_cursor = 0, attr_cursor = 0, tri_cursor = 0, bone_cursor = 0;
 			u64 uv_cursor[kMaxUvSets] = {};
 			for (u32 q = page_segment_offsets[page_index]; q < page_segment_offsets[page_index + 1]; ++q)
 			{
@@ -1656,6 +1781,8 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 					job.pos_cursor = pos_cursor;
 					job.attr_cursor = attr_cursor;
 					job.tri_cursor = tri_cursor;
+					job.bone_cursor = bone_cursor;
+					bone_cursor += job.bone_count;
 					pos_cursor += job.vertex_count * 12;
 					attr_cursor += job.vertex_count;
 					tri_cursor += job.tri_count * 3;
@@ -1700,9 +1827,9 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	if (U)
 		dev_h2d(d_uv_jobs, uv_jobs.data(), uv_jobs.size() * sizeof(UvJob));
 #ifdef CLODB_EMU
-	LAUNCH(k_write_pages, M, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors);
+	LAUNCH(k_write_pages, M, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors, d_bone_scratch);
 #else
-	LAUNCH_GRID(k_write_pages_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors);
+	LAUNCH_GRID(k_write_pages_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors, d_bone_scratch);
 #endif
 	lap("page writer kernel");
 	out.pages.reserve(total_bytes + 16);

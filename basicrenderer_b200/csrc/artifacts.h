@@ -47,6 +47,11 @@ struct DeviceGeometry
 	u32 uv_set_count = 0;
 	const float* uv_values[kMaxUvSets] = {}; // u at [i * uv_stride], v at [i * uv_stride + 1]
 	u32 uv_stride[kMaxUvSets] = {};          // in floats
+	// skinned meshes: the importer's second vertex stream (position f32x3, normal f32x3, joints u32x4 x2, weights f32x4 x2;
+	// ClusterLODUtilities.cpp:50-56, :1091-1120); only the page writer reads it
+	const u8* skinning_vertices = nullptr;
+	u32 skinning_stride = 0;
+	size_t skinning_vertex_count = 0;
 	DeviceMesh mesh;
 	// MikkTSpace tangents are generated inside every build call, as the reference does (ClusterLODUtilities.cpp:5359-5366):
 	// tangents4 = float4 per vertex scratch, attribute columns [tangent_column, +4) of mesh.attributes receive them

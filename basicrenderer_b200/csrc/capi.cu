@@ -1123,6 +1123,18 @@ static clodb200_device_geometry* upload_geometry_locked(const clodb200_geometry&
 			geo.uv_stride[s] = 2;
 		}
 
+		// skinned meshes: the second vertex stream only feeds the page writer (joints, weights, bone lists)
+		if (g.skinning_vertices && g.skinning_vertex_bytes && g.skinning_vertex_stride)
+		{
+			if (g.skinning_vertex_stride % 4)
+				throw Error("clodb200: the skinning vertex stride must be a multiple of 4");
+			u8* dsk = static_cast<u8*>(block_alloc(g.skinning_vertex_bytes, dg->allocations));
+			dev_h2d(dsk, g.skinning_vertices, g.skinning_vertex_bytes);
+			geo.skinning_vertices = dsk;
+			geo.skinning_stride = g.skinning_vertex_stride;
+			geo.skinning_vertex_count = g.skinning_vertex_bytes / g.skinning_vertex_stride;
+		}
+
 		// simplification attribute stream (ClusterLODUtilities.cpp:5359-5410): normals x3, then tangent xyz + sign
 		const bool has_normals = (g.vertex_flags & kVertexNormals) != 0 && g.vertex_stride >= 24;
 		const bool has_texcoords = (g.vertex_flags & kVertexTexcoords) != 0 && g.vertex_stride >= 32;

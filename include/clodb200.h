@@ -243,7 +243,12 @@ typedef struct clodb200_uv_set
  * colour f32x3 if VERTEX_COLORS), vertex_flags the VertexFlags bits (Mesh/VertexFlags.h). `tangents` is normally NULL:
  * when the stream has normals and texcoords and normal-attribute simplification is on, the MikkTSpace tangent stream is
  * generated on the device as the reference's GenerateMikkTangents does inside its call (:655-737, :5359-5366). A
- * non-NULL `tangents` (float4 per vertex) overrides the generator. Skinned meshes are not supported. */
+ * non-NULL `tangents` (float4 per vertex) overrides the generator.
+ * Skinned meshes: `skinning_vertices` is the importer's second stream (MeshIngestBuilder::AppendSkinningVertexBytes; position f32x3,
+ * normal f32x3, joints u32x4 x2, weights f32x4 x2 = PackedSkinningInfluences at byte 24, skinning_vertex_stride >= 88), NULL when the
+ * mesh is not skinned. It only feeds the pages: joint and weight arrays per meshlet vertex and the sorted per-meshlet bone lists
+ * (ClusterLODUtilities.cpp:1091-1120, 1240-1265, 1677-1711); skinning_vertex_bytes is the size of the stream (vertices beyond it
+ * read as zero influences, :1107-1110). */
 typedef struct clodb200_geometry
 {
 	const void* vertices;
@@ -255,6 +260,9 @@ typedef struct clodb200_geometry
 	const clodb200_uv_set* uv_sets;
 	size_t uv_set_count;
 	const float* tangents;
+	const void* skinning_vertices;
+	size_t skinning_vertex_bytes;
+	unsigned int skinning_vertex_stride;
 } clodb200_geometry;
 
 #define CLODB200_VERTEX_COLORS 1u

@@ -6,7 +6,7 @@
 // (Import/GlTFGeometryExtractor.cpp:1025-1298, Import/USDGeometryExtractor.cpp:743-859) switches by changing a namespace.
 // Differences: BuildClusterLODArtifacts() returns an owning handle to the artifacts held by the library (named arrays of
 // the reference's PODs, see clodb200_artifactsGet) instead of a ClusterLODPrebuildArtifacts value; Build() (the
-// renderer-side GPU Mesh object) is out of scope; skinned meshes are rejected by the library.
+// renderer-side GPU Mesh object) is out of scope.
 #pragma once
 
 #include "clodb200.h"
@@ -158,8 +158,6 @@ public:
 	// failure, as the reference throws from its validation (ClusterLODUtilities.cpp:4637, 5252, 5726).
 	ClusterLODPrebuildArtifacts BuildClusterLODArtifacts() const
 	{
-		if (!m_skinningVertices.empty())
-			throw std::runtime_error("clodb200: skinned meshes are not supported");
 		std::vector<clodb200_uv_set> sets(m_uvSets.size());
 		for (size_t i = 0; i < m_uvSets.size(); ++i)
 		{
@@ -176,6 +174,9 @@ public:
 		g.uv_sets = sets.empty() ? nullptr : sets.data();
 		g.uv_set_count = sets.size();
 		g.tangents = nullptr;
+		g.skinning_vertices = m_skinningVertices.empty() ? nullptr : m_skinningVertices.data();
+		g.skinning_vertex_bytes = m_skinningVertices.size();
+		g.skinning_vertex_stride = m_skinningVertexSize;
 		clodb200_artifacts* a = clodb200_buildArtifacts(&g, &m_clusterLODBuilderSettings);
 		if (!a)
 			throw std::runtime_error(clodb200_last_error());

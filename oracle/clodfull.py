@@ -47,6 +47,8 @@ def _lib(ours: bool):
         lib = C.CDLL(os.path.join(_HERE, "_ref", "libclodref_full_ours.so" if ours else "libclodref_full.so"))
         lib.clodfull_build.restype = C.c_void_p
         lib.clodfull_build.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint]
+        lib.clodfull_build_skinned.restype = C.c_void_p
+        lib.clodfull_build_skinned.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint]
         lib.clodfull_error.restype = C.c_char_p
         lib.clodfull_error.argtypes = [C.c_void_p]
         lib.clodfull_seconds.restype = C.c_double
@@ -114,14 +116,19 @@ def interleave(positions, normals, uvs=None) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate(cols, axis=1))
 
 
-def build(vertices: np.ndarray, indices: np.ndarray, flags: int = VERTEX_NORMALS, threads: int = 1, clodb200_lib: str | None = None) -> Artifacts:
+def build(vertices: np.ndarray, indices: np.ndarray, flags: int = VERTEX_NORMALS, threads: int = 1, clodb200_lib: str | None = None, skinning: np.ndarray | None = None) -> Artifacts:
     ours = clodb200_lib is not None
     if ours:
         os.environ["CLODB200_LIB"] = clodb200_lib
     lib = _lib(ours)
     vertices = np.ascontiguousarray(vertices, np.float32)
     indices = np.ascontiguousarray(indices, np.uint32)
-    h = lib.clodfull_build(vertices.ctypes.data_as(C.c_void_p), vertices.shape[0], vertices.shape[1] * 4, indices.ctypes.data_as(C.c_void_p), indices.size, flags, threads)
+    if skinning is not None:
+        skinning = np.ascontiguousarray(skinning, np.uint8)
+        h = lib.clodfull_build_skinned(vertices.ctypes.data_as(C.c_void_p), vertices.shape[0], vertices.shape[1] * 4, indices.ctypes.data_as(C.c_void_p), indices.size, flags, threads,
+                                       skinning.ctypes.data_as(C.c_void_p), skinning.size, skinning.shape[1])
+    else:
+        h = lib.clodfull_build(vertices.ctypes.data_as(C.c_void_p), vertices.shape[0], vertices.shape[1] * 4, indices.ctypes.data_as(C.c_void_p), indices.size, flags, threads)
     try:
         err = lib.clodfull_error(h).decode()
         if err:

@@ -69,7 +69,17 @@ extern "C"
 
 // vertices: interleaved per VertexLayout.h (pos f32x3 @0, normal f32x3 @12[, uv f32x2 @24][, color f32x3]); flags = VertexFlags.
 // threads: 0/1 = serial (scheduler left uninitialised, ClusterLODUtilities.cpp:5619), n > 1 = n worker threads.
+void* clodfull_build_skinned(const unsigned char* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count, unsigned int flags, unsigned int threads,
+    const unsigned char* skinning_vertices, size_t skinning_bytes, unsigned int skinning_stride);
+
 void* clodfull_build(const unsigned char* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count, unsigned int flags, unsigned int threads)
+{
+	return clodfull_build_skinned(vertices, vertex_count, vertex_stride, indices, index_count, flags, threads, nullptr, 0, 0);
+}
+
+// skinning_vertices: the importer's second vertex stream (MeshIngestBuilder::AppendSkinningVertexBytes), or null
+void* clodfull_build_skinned(const unsigned char* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count, unsigned int flags, unsigned int threads,
+    const unsigned char* skinning_vertices, size_t skinning_bytes, unsigned int skinning_stride)
 {
 	Handle* h = new Handle();
 	try
@@ -85,7 +95,10 @@ void* clodfull_build(const unsigned char* vertices, size_t vertex_count, unsigne
 		std::vector<uint32_t> idx(indices, indices + index_count);
 		std::vector<MeshUvSetData> uvSets;
 		auto t0 = std::chrono::steady_clock::now();
-		ClusterLODPrebuildArtifacts a = BuildClusterLODArtifactsFromGeometry(v, vertex_stride, nullptr, 0, idx, uvSets, flags, mesh_mode_settings());
+		std::vector<std::byte> skin;
+		if (skinning_vertices && skinning_bytes)
+			skin.assign(reinterpret_cast<const std::byte*>(skinning_vertices), reinterpret_cast<const std::byte*>(skinning_vertices) + skinning_bytes);
+		ClusterLODPrebuildArtifacts a = BuildClusterLODArtifactsFromGeometry(v, vertex_stride, skin.empty() ? nullptr : &skin, skinning_stride, idx, uvSets, flags, mesh_mode_settings());
 		h->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 		tsm.Cleanup();
 

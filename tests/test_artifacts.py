@@ -121,3 +121,50 @@ def test_cache_files_round_trip(lib, meshes, tmp_path):
     for i, p in enumerate(pages):
         assert np.array_equal(np.frombuffer(p, np.uint8), a.page(i))
         assert int(meta["pageDiskLocators"][i]["blobSizeBytes"]) == len(p)
+
+
+def _skinning(m, bones=37, seed=9, zero_fraction=0.3):
+    """Random skinning influences: up to 8 joints per vertex out of `bones`, a share of the weights exactly zero (those joints must
+    not enter the meshlet bone lists), one vertex in ten without any positive weight."""
+    rng = np.random.default_rng(seed)
+    V = m.vertex_count
+    joints = rng.integers(0, bones, (V, 8)).astype(np.uint32)
+    weights = rng.random((V, 8), dtype=np.float32)
+    weights[rng.random((V, 8)) < zero_fraction] = 0.0
+    weights[rng.random(V) < 0.1] = 0.0
+    weights[0, 0] = -0.5  # negative weights do not count either (weight > 0.0f)
+    return art.skinning_stream(m.positions, m.normals, joints, weights)
+
+
+@pytest.mark.parametrize("name", ["grid64", "torus"])
+def test_skinned_artifacts_identical_to_reference_builder(lib, full_oracle, meshes, name):
+    """Skinned meshes (ClusterLODUtilities.cpp:1091-1120, 1240-1265, 1677-1711): joint and weight arrays per meshlet vertex, sorted
+    per-meshlet bone lists, boneListOffset / boneCount in the descriptors, joints | weights in the page attribute mask; the extra
+    64 bytes per vertex also move the page splits."""
+    m = meshes[name]
+    v = art.interleave(m.positions, m.normals)
+    skin = _skinning(m)
+    ref = full_oracle.build(v, m.indices, clodb200_lib=lib.path, skinning=skin)
+    ours = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS | art.VERTEX_SKINNED, skinning=skin)
+    _assert_identical(ref, ours)
+    header = ours.page(0)[:64].view(np.uint32)
+    assert header[2] & 0b0110 == 0b0110 and header[9] != 0 and header[10] != 0  # attribute mask, joint / weight array offsets
+    plain = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS)
+    assert ours.meshPageOffsets[-1] > plain.meshPageOffsets[-1]
+
+
+def test_skinned_multi_group_and_short_skinning_stream(lib, full_oracle):
+    """Several groups and pages per level; a skinning stream shorter than the vertex stream (vertices beyond it read as zero
+    influences, :1107-1110); the resident path gives the same bytes."""
+    m = meshgen.grid(200, seed=21)
+    v = art.interleave(m.positions, m.normals)
+    skin = _skinning(m, bones=300, seed=4)[: m.vertex_count - 1234]
+    flags = art.VERTEX_NORMALS | art.VERTEX_SKINNED
+    ref = full_oracle.build(v, m.indices, flags=flags, clodb200_lib=lib.path, skinning=skin)
+    ours = lib.build_artifacts(v, m.indices, flags, skinning=skin)
+    assert np.bincount(ours.groups["depth"]).max() > 1
+    _assert_identical(ref, ours)
+    h = lib.upload_geometry(v, m.indices, flags, skinning=skin)
+    again = lib.build_artifacts_resident(h)
+    lib.free_geometry(h)
+    _assert_identical(ours, again)
