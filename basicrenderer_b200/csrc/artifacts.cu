@@ -302,6 +302,88 @@ DEVFN bool group_vertex_insert(u64* table, u64 mask, u32 group, u32 v)
 	}
 }
 
+// slot of an inserted (group, vertex) pair (the pre-pass inserted every pair the meshlets reference)
+DEVFN u64 group_vertex_slot(const u64* table, u64 mask, u32 group, u32 v)
+{
+	u64 key = (u64(group) << 32) | v;
+	u64 h = (key * 0x9E3779B97F4A7C15ull) >> 20;
+	for (;;)
+	{
+		h &= mask;
+		if (table[h] == key)
+			return h;
+		h++;
+	}
+}
+
+// RecalculateGroupNormals (CLU.cpp:739-822, preserveImportedNormals = false): per group vertex the UNNORMALISED face normals of the
+// group's triangles, summed in the reference's order - meshlets in bucket order, triangles in meshlet order - so the float sums
+// carry the same bits. One thread per group walks its meshlets sequentially (groups are independent); the sums live at the
+// (group, vertex) slots of the pre-pass table. Off the default path (the reference never clears preserveImportedNormals itself).
+struct GroupSpan
+{
+	u32 first, count; // meshlets [first, first + count) in group-bucket order
+};
+
+KERNEL k_group_normal_sums(const GroupSpan* __restrict__ spans, u32 G, const MeshletJob* __restrict__ jobs, LevelTable levels, VertexStreams vs, const u64* __restrict__ table, u64 table_mask, float* sums3)
+{
+	size_t g = GTID;
+	if (g >= G)
+		return;
+	const GroupSpan span = spans[g];
+	for (u32 m = span.first; m < span.first + span.count; ++m)
+	{
+		const MeshletJob job = jobs[m];
+		const u32* idx = levels.tri[job.level] + size_t(job.tri_begin) * 3;
+		for (u32 t = 0; t < job.tri_count; ++t)
+		{
+			const u32 v0 = idx[t * 3 + 0], v1 = idx[t * 3 + 1], v2 = idx[t * 3 + 2];
+			const float* p0 = reinterpret_cast<const float*>(vs.vertices + size_t(v0) * vs.stride);
+			const float* p1 = reinterpret_cast<const float*>(vs.vertices + size_t(v1) * vs.stride);
+			const float* p2 = reinterpret_cast<const float*>(vs.vertices + size_t(v2) * vs.stride);
+			const float e10x = p1[0] - p0[0], e10y = p1[1] - p0[1], e10z = p1[2] - p0[2];
+			const float e20x = p2[0] - p0[0], e20y = p2[1] - p0[1], e20z = p2[2] - p0[2];
+			const float nx = e10y * e20z - e10z * e20y, ny = e10z * e20x - e10x * e20z, nz = e10x * e20y - e10y * e20x;
+			const u32 vv[3] = {v0, v1, v2};
+			for (int c = 0; c < 3; ++c)
+			{
+				float* acc = sums3 + group_vertex_slot(table, table_mask, u32(g), vv[c]) * 3;
+				acc[0] += nx;
+				acc[1] += ny;
+				acc[2] += nz;
+			}
+		}
+	}
+}
+
+// NormalizeOrFallback (CLU.cpp:528-548) of the group sum with the source normal as fallback
+DEVFN void recomputed_normal(const float* sum3, const float* source, float& x, float& y, float& z)
+{
+	const float len_sq = sum3[0] * sum3[0] + sum3[1] * sum3[1] + sum3[2] * sum3[2];
+	if (len_sq <= 1e-20f)
+	{
+		const float fallback_sq = source[0] * source[0] + source[1] * source[1] + source[2] * source[2];
+		if (fallback_sq <= 1e-20f)
+		{
+			x = 0.0f, y = 0.0f, z = 1.0f;
+			return;
+		}
+		const float inv = 1.0f / sqrtf(fallback_sq);
+		x = source[0] * inv, y = source[1] * inv, z = source[2] * inv;
+		return;
+	}
+	const float inv = 1.0f / sqrtf(len_sq);
+	x = sum3[0] * inv, y = sum3[1] * inv, z = sum3[2] * inv;
+}
+
+// what the page writer needs to replace the source normals by the recomputed ones (all null/zero on the default path)
+struct NormalRecompute
+{
+	const u64* table;
+	u64 table_mask;
+	const float* sums3;
+};
+
 // ---- scalar kernels (one thread per meshlet): the emulation build runs these ----------------------------------------------
 struct LocalTable
 {
@@ -399,7 +481,7 @@ DEVFN void write_descriptor(u32* desc, const MeshletJob& job)
 }
 
 KERNEL k_write_pages(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, const PageRecord* __restrict__ pages, const UvJob* __restrict__ uv_jobs, u8* out, u32* errors,
-    const u32* __restrict__ bone_scratch)
+    const u32* __restrict__ bone_scratch, NormalRecompute recompute)
 {
 	size_t m = GTID;
 	if (m >= M)
@@ -439,7 +521,14 @@ KERNEL k_write_pages(const MeshletJob* __restrict__ jobs, u32 M, LevelTable leve
 		if (nrm)
 		{
 			const float* n = reinterpret_cast<const float*>(v + vs.normal_offset);
-			nrm[vi] = pack_oct_normal(n[0], n[1], n[2]);
+			if (recompute.sums3)
+			{
+				float x, y, z;
+				recomputed_normal(recompute.sums3 + group_vertex_slot(recompute.table, recompute.table_mask, job.group, t.vertices[vi]) * 3, n, x, y, z);
+				nrm[vi] = pack_oct_normal(x, y, z);
+			}
+			else
+				nrm[vi] = pack_oct_normal(n[0], n[1], n[2]);
 		}
 		if (col)
 		{
@@ -601,7 +690,7 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_meshlet_prepass_warp(c
 }
 
 static __global__ void __launch_bounds__(MW_WARPS * 32) k_write_pages_warp(const MeshletJob* __restrict__ jobs, u32 M, LevelTable levels, VertexStreams vs, const PageRecord* __restrict__ pages, const UvJob* __restrict__ uv_jobs, u8* out, u32* errors,
-    const u32* __restrict__ bone_scratch)
+    const u32* __restrict__ bone_scratch, NormalRecompute recompute)
 {
 	__shared__ WarpTable s_tables[MW_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -663,7 +752,15 @@ static __global__ void __launch_bounds__(MW_WARPS * 32) k_write_pages_warp(const
 		if (nrm)
 		{
 			const float* nn = reinterpret_cast<const float*>(v + vs.normal_offset);
-			nrm[vi] = pack_oct_normal(__ldg(nn), __ldg(nn + 1), __ldg(nn + 2));
+			if (recompute.sums3)
+			{
+				const float source[3] = {__ldg(nn), __ldg(nn + 1), __ldg(nn + 2)};
+				float x, y, z;
+				recomputed_normal(recompute.sums3 + group_vertex_slot(recompute.table, recompute.table_mask, job.group, t.vertices[vi]) * 3, source, x, y, z);
+				nrm[vi] = pack_oct_normal(x, y, z);
+			}
+			else
+				nrm[vi] = pack_oct_normal(__ldg(nn), __ldg(nn + 1), __ldg(nn + 2));
 		}
 		if (col)
 		{
@@ -1334,8 +1431,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	const bool has_texcoords = (flags & kVertexTexcoords) != 0 && stride >= 32;
 	const u32 color_offset = 24 + ((flags & kVertexTexcoords) ? 8u : 0u);
 	const bool has_colors = (flags & kVertexColors) != 0 && stride >= color_offset + 12;
-	if (has_normals && !settings.preserve_imported_normals)
-		throw Error("clodb200: preserveImportedNormals = false (RecalculateGroupNormals, ClusterLODUtilities.cpp:739-822) is not implemented");
+	const bool recompute_normals = has_normals && !settings.preserve_imported_normals; // CLU.cpp:5352
 
 	// builder configuration (CLU.cpp:5426-5460)
 	Config config;
@@ -1826,10 +1922,23 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	dev_h2d(d_pages, pages.data(), size_t(page_count) * sizeof(PageRecord));
 	if (U)
 		dev_h2d(d_uv_jobs, uv_jobs.data(), uv_jobs.size() * sizeof(UvJob));
+	NormalRecompute recompute = {nullptr, 0, nullptr};
+	if (recompute_normals)
+	{
+		std::vector<GroupSpan> spans(G);
+		for (u32 g = 0; g < G; ++g)
+			spans[g] = GroupSpan{sink.groups[g].first, sink.groups[g].count};
+		GroupSpan* d_spans = temp.alloc<GroupSpan>(G);
+		float* d_sums = temp.alloc<float>(size_t(table_size) * 3);
+		dev_h2d(d_spans, spans.data(), size_t(G) * sizeof(GroupSpan));
+		dev_memset(d_sums, 0, size_t(table_size) * 12);
+		LAUNCH(k_group_normal_sums, G, d_spans, G, d_jobs, levels, vs, d_table, table_size - 1, d_sums);
+		recompute = NormalRecompute{d_table, table_size - 1, d_sums};
+	}
 #ifdef CLODB_EMU
-	LAUNCH(k_write_pages, M, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors, d_bone_scratch);
+	LAUNCH(k_write_pages, M, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors, d_bone_scratch, recompute);
 #else
-	LAUNCH_GRID(k_write_pages_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors, d_bone_scratch);
+	LAUNCH_GRID(k_write_pages_warp, (M + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, d_jobs, M, levels, vs, d_pages, d_uv_jobs, d_out, d_errors, d_bone_scratch, recompute);
 #endif
 	lap("page writer kernel");
 	out.pages.reserve(total_bytes + 16);

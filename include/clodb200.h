@@ -215,7 +215,8 @@ void clodb200_recordFree(clodb200_record* record);
 
 /* The ClusterLODBuilderSettings fields that are live in mesh mode (ClusterLODTypes.h:187-212). The voxel fallback is not
  * built: the call behaves as enableVoxelFallback = false / voxelFallbackMode = MeshOnly (CLodCacheTool --clod-voxel-mode=mesh).
- * preserveImportedNormals = 0 is rejected (group normal recomputation is not implemented). */
+ * preserveImportedNormals = 0 recomputes the page normals per group from the group's triangles (RecalculateGroupNormals,
+ * ClusterLODUtilities.cpp:739-822; one GPU thread per group, not tuned: the reference itself never clears the flag). */
 typedef struct clodb200_builder_settings
 {
 	float lodErrorMergePrevious;

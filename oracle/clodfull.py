@@ -116,13 +116,15 @@ def interleave(positions, normals, uvs=None) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate(cols, axis=1))
 
 
-def build(vertices: np.ndarray, indices: np.ndarray, flags: int = VERTEX_NORMALS, threads: int = 1, clodb200_lib: str | None = None, skinning: np.ndarray | None = None) -> Artifacts:
+def build(vertices: np.ndarray, indices: np.ndarray, flags: int = VERTEX_NORMALS, threads: int = 1, clodb200_lib: str | None = None, skinning: np.ndarray | None = None,
+          recompute_normals: bool = False) -> Artifacts:
     ours = clodb200_lib is not None
     if ours:
         os.environ["CLODB200_LIB"] = clodb200_lib
     lib = _lib(ours)
     vertices = np.ascontiguousarray(vertices, np.float32)
     indices = np.ascontiguousarray(indices, np.uint32)
+    lib.clodfull_set_options(1 if recompute_normals else 0)
     if skinning is not None:
         skinning = np.ascontiguousarray(skinning, np.uint8)
         h = lib.clodfull_build_skinned(vertices.ctypes.data_as(C.c_void_p), vertices.shape[0], vertices.shape[1] * 4, indices.ctypes.data_as(C.c_void_p), indices.size, flags, threads,

@@ -72,6 +72,13 @@ extern "C"
 void* clodfull_build_skinned(const unsigned char* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count, unsigned int flags, unsigned int threads,
     const unsigned char* skinning_vertices, size_t skinning_bytes, unsigned int skinning_stride);
 
+// options for the next clodfull_build* call on this process: bit 0 = preserveImportedNormals false (RecalculateGroupNormals)
+static unsigned int g_build_options = 0;
+void clodfull_set_options(unsigned int options)
+{
+	g_build_options = options;
+}
+
 void* clodfull_build(const unsigned char* vertices, size_t vertex_count, unsigned int vertex_stride, const unsigned int* indices, size_t index_count, unsigned int flags, unsigned int threads)
 {
 	return clodfull_build_skinned(vertices, vertex_count, vertex_stride, indices, index_count, flags, threads, nullptr, 0, 0);
@@ -98,7 +105,10 @@ void* clodfull_build_skinned(const unsigned char* vertices, size_t vertex_count,
 		std::vector<std::byte> skin;
 		if (skinning_vertices && skinning_bytes)
 			skin.assign(reinterpret_cast<const std::byte*>(skinning_vertices), reinterpret_cast<const std::byte*>(skinning_vertices) + skinning_bytes);
-		ClusterLODPrebuildArtifacts a = BuildClusterLODArtifactsFromGeometry(v, vertex_stride, skin.empty() ? nullptr : &skin, skinning_stride, idx, uvSets, flags, mesh_mode_settings());
+		ClusterLODBuilderSettings build_settings = mesh_mode_settings();
+		if (g_build_options & 1u)
+			build_settings.preserveImportedNormals = false;
+		ClusterLODPrebuildArtifacts a = BuildClusterLODArtifactsFromGeometry(v, vertex_stride, skin.empty() ? nullptr : &skin, skinning_stride, idx, uvSets, flags, build_settings);
 		h->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 		tsm.Cleanup();
 

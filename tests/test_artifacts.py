@@ -168,3 +168,31 @@ def test_skinned_multi_group_and_short_skinning_stream(lib, full_oracle):
     again = lib.build_artifacts_resident(h)
     lib.free_geometry(h)
     _assert_identical(ours, again)
+
+
+@pytest.mark.parametrize("name", ["grid64", "ico24"])
+def test_recomputed_group_normals(lib, full_oracle, meshes, name):
+    """preserveImportedNormals = false (RecalculateGroupNormals, ClusterLODUtilities.cpp:739-822): the page normals are the
+    normalised sums of the group's face normals, accumulated in the reference's order (bit-exact), with the source normal as the
+    fallback for degenerate sums."""
+    m = meshes[name]
+    normals = m.normals.copy()
+    normals[::7] = 0.0  # fallback of the fallback: (0, 0, 1)
+    v = art.interleave(m.positions, normals)
+    st = lib.default_builder_settings()
+    st.preserveImportedNormals = 0
+    ours = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS, settings=st)
+    ref = full_oracle.build(v, m.indices, clodb200_lib=lib.path, recompute_normals=True)
+    _assert_identical(ref, ours)
+    kept = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS)
+    assert not np.array_equal(kept.meshPages, ours.meshPages)
+
+
+def test_recomputed_group_normals_multi_group(lib, full_oracle):
+    m = meshgen.grid(200, seed=3)
+    v = art.interleave(m.positions, m.normals)
+    st = lib.default_builder_settings()
+    st.preserveImportedNormals = 0
+    ours = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS, settings=st)
+    assert np.bincount(ours.groups["depth"]).max() > 1
+    _assert_identical(full_oracle.build(v, m.indices, clodb200_lib=lib.path, recompute_normals=True), ours)
