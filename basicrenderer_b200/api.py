@@ -489,6 +489,10 @@ class ClodLib:
         finally:
             L.clodb200_commGatherFree(handle)
 
+    def cache_probe(self, directory: str, metadata_file_name: str, source_identifier: str = "", prim_path: str = "", subset_name: str = "", build_config_hash: int = 0) -> bool:
+        self._lib.clodb200_cacheProbe.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64]
+        return bool(self._lib.clodb200_cacheProbe(directory.encode(), metadata_file_name.encode(), source_identifier.encode(), prim_path.encode(), subset_name.encode(), build_config_hash))
+
     def timer_start(self):
         self._lib.clodb200_timerStart()
 

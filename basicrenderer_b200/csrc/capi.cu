@@ -1418,6 +1418,97 @@ int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char*
 	}
 }
 
+// Skip-if-cached (CLodCacheLoader::TryLoadPrebuilt -> CLodCache::TryLoad, CLodCacheLoader.cpp:218-234, CLodCache.cpp:635-713):
+// is there a cache for this identity and build configuration that the loader would accept? Walks the metadata blob the way
+// DeserializeMetadata does (CLodCache.cpp:209-250) and applies its acceptance rules: schema version, build hash and identity equal,
+// blob consumed exactly, container present with the container magic/version and one locator per mesh page. No GPU involved.
+int clodb200_cacheProbe(const char* directory, const char* metadata_file_name, const char* source_identifier, const char* prim_path, const char* subset_name, uint64_t build_config_hash)
+{
+	if (!directory || !metadata_file_name)
+		return 0;
+	const std::string dir(directory);
+	FILE* f = fopen((dir + "/" + metadata_file_name).c_str(), "rb");
+	if (!f)
+		return 0;
+	std::vector<u8> blob;
+	u8 chunk[65536];
+	for (size_t n; (n = fread(chunk, 1, sizeof(chunk), f)) > 0;)
+		blob.insert(blob.end(), chunk, chunk + n);
+	fclose(f);
+	size_t off = 0;
+	bool ok = true;
+	auto pod = [&](void* out, size_t bytes) {
+		if (!ok || off + bytes > blob.size())
+		{
+			ok = false;
+			return;
+		}
+		memcpy(out, blob.data() + off, bytes);
+		off += bytes;
+	};
+	auto skip_vector = [&](size_t element) -> u64 {
+		u64 count = 0;
+		pod(&count, 8);
+		if (!ok || count > (blob.size() - off) / (element ? element : 1))
+		{
+			ok = false;
+			return 0;
+		}
+		off += size_t(count) * element;
+		return count;
+	};
+	auto string = [&]() -> std::string {
+		u64 n = 0;
+		pod(&n, 8);
+		if (!ok || n > blob.size() - off)
+		{
+			ok = false;
+			return std::string();
+		}
+		std::string s(reinterpret_cast<const char*>(blob.data() + off), size_t(n));
+		off += size_t(n);
+		return s;
+	};
+	u32 schema = 0;
+	u64 hash = 0, hash2 = 0;
+	pod(&schema, 4);
+	pod(&hash, 8);
+	skip_vector(76); // groups
+	skip_vector(16); // segments
+	skip_vector(16); // segmentBounds
+	off += 16;       // objectBoundingSphere
+	u8 has_chunks = 0;
+	pod(&has_chunks, 1);
+	if (has_chunks)
+		skip_vector(20);
+	skip_vector(16); // groupDiskLocators
+	const u64 page_locators = skip_vector(16);
+	skip_vector(4); // groupPageReferences
+	skip_vector(4); // groupPageReferenceOffsets
+	u32 page_counts[3] = {0, 0, 0};
+	pod(page_counts, 12);
+	const std::string src = string(), prim = string(), subset = string();
+	pod(&hash2, 8);
+	const std::string container = string();
+	skip_vector(64); // nodes
+	skip_vector(8);  // lodNodeRanges
+	skip_vector(4);  // lodLevelRoots
+	off += 8;        // maxDepth, maxTraversalDepth
+	if (!ok || off != blob.size() || schema != 47 || hash != build_config_hash || hash2 != build_config_hash)
+		return 0;
+	if (src != (source_identifier ? source_identifier : "") || prim != (prim_path ? prim_path : "") || subset != (subset_name ? subset_name : ""))
+		return 0;
+	if (page_locators != u64(page_counts[0]) + page_counts[2])
+		return 0;
+	FILE* c = fopen((dir + "/" + container).c_str(), "rb");
+	if (!c)
+		return 0;
+	u32 header[4] = {0, 0, 0, 0};
+	size_t got = fread(header, 1, sizeof(header), c);
+	fclose(c);
+	return got == sizeof(header) && header[0] == 0x444F4C43u && header[1] == 4u && header[3] == u32(page_locators) ? 1 : 0;
+}
+
 #ifndef CLODB_EMU
 static thread_local cudaEvent_t g_timer_start = nullptr, g_timer_stop = nullptr;
 #endif

@@ -299,6 +299,11 @@ void clodb200_artifactsFree(clodb200_artifacts* artifacts);
  * the caller's: the reference derives them with boost::hash_combine (:586-633), which is not restated. */
 int clodb200_artifactsSaveCache(const clodb200_artifacts* artifacts, const char* directory, const char* container_file_name, const char* metadata_file_name,
     const char* source_identifier, const char* prim_path, const char* subset_name, uint64_t build_config_hash);
+/* Skip-if-cached (CLodCacheLoader::TryLoadPrebuilt, CLodCacheLoader.cpp:218-234): 1 when `directory` holds a cache for this identity
+ * and build configuration that the loader's acceptance rules take (CLodCache.cpp:209-250, 635-713: schema 47, build hash and
+ * identity equal, blob consumed exactly, container file present with one locator per mesh page), else 0. Needs no GPU: a batch
+ * tool probes before it uploads a mesh, which is how an interrupted scene build resumes. */
+int clodb200_cacheProbe(const char* directory, const char* metadata_file_name, const char* source_identifier, const char* prim_path, const char* subset_name, uint64_t build_config_hash);
 /* The metadata blob alone: returns the byte count; writes at most `capacity` bytes. */
 size_t clodb200_artifactsSerializeMetadata(const clodb200_artifacts* artifacts, const char* container_file_name, const char* source_identifier, const char* prim_path,
     const char* subset_name, uint64_t build_config_hash, void* buffer, size_t capacity);

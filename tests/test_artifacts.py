@@ -196,3 +196,29 @@ def test_recomputed_group_normals_multi_group(lib, full_oracle):
     ours = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS, settings=st)
     assert np.bincount(ours.groups["depth"]).max() > 1
     _assert_identical(full_oracle.build(v, m.indices, clodb200_lib=lib.path, recompute_normals=True), ours)
+
+
+def test_skip_if_cached_probe(lib, meshes, tmp_path):
+    """clodb200_cacheProbe is the skip-if-cached test of a batch build (CLodCacheLoader::TryLoadPrebuilt,
+    CLodCacheLoader.cpp:218-234): true only for the same identity and build configuration, false for a missing, truncated or
+    foreign cache; the names come from the restated naming functions."""
+    from basicrenderer_b200 import cache
+
+    m = meshes["grid64"]
+    v = art.interleave(m.positions, m.normals)
+    config_hash = cache.build_config_hash({})
+    usdc = cache.cache_file_name("scene.gltf", "/mesh0", "", config_hash)
+    stem = usdc[:-5]
+    d = str(tmp_path)
+    assert not lib.cache_probe(d, stem + ".clodblob", "scene.gltf", "/mesh0", "", config_hash)
+    a = lib.build_artifacts(v, m.indices, art.VERTEX_NORMALS, keep_handle=True)
+    lib.save_cache(a, d, stem + ".clodbin", stem + ".clodblob", "scene.gltf", "/mesh0", "", config_hash)
+    lib.free_artifacts(a)
+    assert lib.cache_probe(d, stem + ".clodblob", "scene.gltf", "/mesh0", "", config_hash)
+    assert not lib.cache_probe(d, stem + ".clodblob", "scene.gltf", "/mesh1", "", config_hash)       # another primitive
+    assert not lib.cache_probe(d, stem + ".clodblob", "scene.gltf", "/mesh0", "", config_hash ^ 1)   # another build configuration
+    blob = (tmp_path / (stem + ".clodblob")).read_bytes()
+    (tmp_path / "cut.clodblob").write_bytes(blob[:-3])
+    assert not lib.cache_probe(d, "cut.clodblob", "scene.gltf", "/mesh0", "", config_hash)            # truncated blob
+    os.remove(tmp_path / (stem + ".clodbin"))
+    assert not lib.cache_probe(d, stem + ".clodblob", "scene.gltf", "/mesh0", "", config_hash)         # container gone
