@@ -81,8 +81,34 @@ auto with_arena_growth(Attempt&& attempt, MayRetry&& may_retry) -> decltype(atte
 			if (e.arena != &g_ws.persist && e.arena != &g_ws.temp)
 				throw;
 			size_t want = std::max(slab.capacity * 2, e.need * 2);
+			// everything in flight (build stream and the asynchronous level downloads) must be done with the slab before it goes
 			dev_sync();
-			slab.init(want);
+			dev_d2h_async_wait();
+#ifndef CLODB_EMU
+			{
+				// never ask for more than the device can give: the old slab is released first, so its bytes count as free
+				size_t free_bytes = 0, total_bytes = 0;
+				if (cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess)
+				{
+					const size_t available = free_bytes + slab.capacity;
+					const size_t margin = size_t(256) << 20;
+					if (e.need + margin > available)
+						throw Error("clodb200: out of device memory (the build needs a " + std::to_string(e.need >> 20) + " MB slab, " + std::to_string(available >> 20) + " MB are available)");
+					want = std::min(want, available - margin);
+				}
+			}
+#endif
+			try
+			{
+				slab.init(want);
+			}
+			catch (const Error&)
+			{
+#ifndef CLODB_EMU
+				cudaGetLastError(); // a failed cudaMalloc leaves its error behind; the next launch check must not trip over it
+#endif
+				throw Error("clodb200: out of device memory while growing a workspace slab to " + std::to_string(want >> 20) + " MB");
+			}
 		}
 	}
 }
