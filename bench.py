@@ -218,6 +218,13 @@ def _pin(a: np.ndarray) -> np.ndarray:
 _PINNED = []
 
 
+def _share_host_cores(world: int, builds_in_flight: int = 1):
+    """Several ranks (and several builds in flight per rank) share the box's host cores: cap the host threads each build's replay
+    stages may use (csrc/rt.cuh host_parallel_for) so that the processes do not oversubscribe them. Must run before the library loads."""
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("CLODB200_HOST_THREADS", str(max(1, min(16, cores // max(1, world * builds_in_flight)))))
+
+
 def _comm_setup(lib, rank, world):
     """The library's own NCCL communicator for the metadata gather: rank 0 makes the id, torch.distributed only ships it."""
     if world == 1:
@@ -358,6 +365,8 @@ def run_scene_batch(args):
     from basicrenderer_b200 import artifacts as art
     from basicrenderer_b200 import load, sharding
 
+    workers = max(1, int(os.environ.get("CLODB200_BENCH_THREADS", 4)))
+    _share_host_cores(world, workers)
     lib = load(local)
     _comm_setup(lib, rank, world)
     count, total = _batch_shape()
@@ -377,7 +386,6 @@ def run_scene_batch(args):
         torch.cuda.synchronize()
 
     # several builds in flight per GPU: every worker thread owns a build context (stream, arenas) inside the library
-    workers = max(1, int(os.environ.get("CLODB200_BENCH_THREADS", 4)))
     # largest meshes first, workers take the next mesh when they finish one (the way the reference's parallel-for hands out primitives)
     order = sorted(range(len(mine)), key=lambda k: -int(host[k][1].size))
     import queue
@@ -479,6 +487,7 @@ def run_ours(args):
 
     from basicrenderer_b200 import load
 
+    _share_host_cores(world)
     lib = load(local)
     _comm_setup(lib, rank, world)
 
