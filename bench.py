@@ -141,7 +141,7 @@ def _sample_clocks(stop_event, out):
                 out.append(parts)
         except Exception:
             pass
-        stop_event.wait(0.2)
+        stop_event.wait(0.5)
 
 
 def _clock_summary(samples):
@@ -272,6 +272,7 @@ def _measure(lib, workload, rank, world, steps, warmup, barrier, with_clocks=Tru
     stop = threading.Event()
     clock_samples = []
     sampler = threading.Thread(target=_sample_clocks, args=(stop, clock_samples), daemon=True)
+    with_clocks = with_clocks and rank == 0  # one nvidia-smi poller per box: NVML queries take driver locks the builds also need
     if with_clocks:
         sampler.start()
     barrier()
@@ -425,7 +426,8 @@ def run_scene_batch(args):
     stop = threading.Event()
     clock_samples = []
     sampler = threading.Thread(target=_sample_clocks, args=(stop, clock_samples), daemon=True)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     barrier()
     lane_launches.clear()
     # the builds run on several streams: the timed region is bracketed by device-wide synchronisations and read on the host
@@ -437,7 +439,8 @@ def run_scene_batch(args):
     launches = sum(lane_launches)
     barrier()
     stop.set()
-    sampler.join()
+    if rank == 0:
+        sampler.join()
     step(False)
     barrier()
     t0 = time.perf_counter()
