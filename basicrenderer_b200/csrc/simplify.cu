@@ -1520,35 +1520,74 @@ KERNEL k_window_check(GroupState* groups, u32 G, u32* any_extend)
 	}
 }
 
-// per sorted position: triangle weight / flip flag / tagged error for the prefix scans behind the serial early-outs
-KERNEL k_cut_inputs(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_group, const float* __restrict__ cand_error, const u8* __restrict__ kind,
-    u32* tri_weight, u32* flip_flag, u64* tagged_error, u32 cand_total)
+// ---- the examined prefixes as one dense index space ---------------------------------------------------------------------
+// Everything after the wavefront (the cut scans, the roll-back, the quadric updates) only concerns the sorted positions the
+// wavefront has examined: per group the prefix [cand_begin, win_end) of its candidates, typically a third of the list. Those
+// prefixes are laid end to end: window position j of group g <-> sorted position cand_begin[g] + (j - woff[g]). The kernels below
+// run over j in [0, W) and find their group by a binary search over the G + 1 offsets (cache resident).
+KERNEL k_window_lengths(const GroupState* __restrict__ groups, u32 G, u32* lengths)
 {
-	size_t k = GTID;
-	if (k >= cand_total)
+	size_t g = GTID;
+	if (g > G)
 		return;
-	u32 c = sorted_cand[k];
-	u8 st = status[k];
-	tri_weight[k] = st == Status_Performed ? (kind[cand_v0[c]] == Kind_Border ? 1u : 2u) : 0u;
-	flip_flag[k] = st == Status_Flip ? 1u : 0u;
-	tagged_error[k] = (u64(cand_group[c] + 1) << 32) | (st == Status_Performed ? u64(__float_as_uint(cand_error[c])) : 0ull);
+	u32 len = 0;
+	if (g < G)
+	{
+		const GroupState& gs = groups[g];
+		if (gs.active && gs.cand_count)
+			len = gs.win_end - gs.cand_begin;
+	}
+	lengths[g] = len; // lengths[G] = 0: after the exclusive scan it holds W
 }
 
-// evaluates the break conditions of performEdgeCollapses (simplifier.cpp:1533-1557) at every sorted position
-KERNEL k_cut_find(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_group, const float* __restrict__ cand_error, GroupState* groups,
-    const u32* __restrict__ tri_prefix, const u32* __restrict__ flip_prefix, const u64* __restrict__ error_prefix, u32 cand_total)
+DEVFN u32 window_group(const u32* __restrict__ woff, u32 G, u32 j)
 {
-	size_t kk = GTID;
-	if (kk >= cand_total)
+	u32 lo = 0, hi = G;
+	while (hi - lo > 1)
+	{
+		u32 mid = (lo + hi) / 2;
+		if (woff[mid] <= j)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
+// per window position: triangle weight / flip flag / tagged error for the prefix scans behind the serial early-outs
+KERNEL k_cut_inputs(const u32* __restrict__ woff, const GroupState* __restrict__ groups, u32 G, u32 W, const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0,
+    const float* __restrict__ cand_error, const u8* __restrict__ kind, u32* tri_weight, u32* flip_flag, u64* tagged_error)
+{
+	size_t jj = GTID;
+	if (jj >= W)
 		return;
-	u32 k = u32(kk);
+	u32 j = u32(jj);
+	u32 g = window_group(woff, G, j);
+	u32 k = groups[g].cand_begin + (j - woff[g]);
 	u32 c = sorted_cand[k];
-	u32 g = cand_group[c];
+	u8 st = status[k];
+	tri_weight[j] = st == Status_Performed ? (kind[cand_v0[c]] == Kind_Border ? 1u : 2u) : 0u;
+	flip_flag[j] = st == Status_Flip ? 1u : 0u;
+	tagged_error[j] = (u64(g + 1) << 32) | (st == Status_Performed ? u64(__float_as_uint(cand_error[c])) : 0ull);
+}
+
+// evaluates the break conditions of performEdgeCollapses (simplifier.cpp:1533-1557) at every examined sorted position
+KERNEL k_cut_find(const u32* __restrict__ woff, u32 G, u32 W, const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const float* __restrict__ cand_error, GroupState* groups,
+    const u32* __restrict__ tri_prefix, const u32* __restrict__ flip_prefix, const u64* __restrict__ error_prefix)
+{
+	size_t jj = GTID;
+	if (jj >= W)
+		return;
+	u32 j = u32(jj);
+	u32 g = window_group(woff, G, j);
 	GroupState& gs = groups[g];
+	u32 wbase = woff[g];
 	u32 base = gs.cand_begin;
+	u32 k = base + (j - wbase);
+	u32 c = sorted_cand[k];
 	u32 goal = gs.tri_count - gs.target_tris; // triangle_collapse_goal
-	u32 tris_before = tri_prefix[k] - tri_prefix[base];
-	u32 flips_before = flip_prefix[k] - flip_prefix[base];
+	u32 tris_before = tri_prefix[j] - tri_prefix[wbase];
+	u32 flips_before = flip_prefix[j] - flip_prefix[wbase];
 	float error = cand_error[c];
 
 	bool stop = false;
@@ -1558,7 +1597,7 @@ KERNEL k_cut_find(const u32* __restrict__ sorted_cand, const u8* __restrict__ st
 	{
 		u32 edge_goal = goal / 2 + flips_before;
 		float error_goal = edge_goal < gs.cand_count ? 1.5f * cand_error[sorted_cand[base + edge_goal]] : FLT_MAX;
-		u64 pe = error_prefix[k];
+		u64 pe = error_prefix[j];
 		float result_error = gs.result_error;
 		if (u32(pe >> 32) == g + 1)
 		{
@@ -1577,17 +1616,18 @@ KERNEL k_cut_find(const u32* __restrict__ sorted_cand, const u8* __restrict__ st
 }
 
 // roll back collapses past the cut, count the accepted ones and fold their errors into the group result
-KERNEL k_cut_apply(const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const u32* __restrict__ cand_group, const float* __restrict__ cand_error,
-    const u32* __restrict__ wedge, const u8* __restrict__ kind, GroupState* groups, u32* group_collapses, u32* group_error_bits, u32* collapse_remap, u32 cand_total)
+KERNEL k_cut_apply(const u32* __restrict__ woff, u32 G, u32 W, const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const float* __restrict__ cand_error,
+    const u32* __restrict__ wedge, const u8* __restrict__ kind, GroupState* groups, u32* group_collapses, u32* group_error_bits, u32* collapse_remap)
 {
-	size_t kk = GTID;
-	if (kk >= cand_total)
+	size_t jj = GTID;
+	if (jj >= W)
 		return;
-	u32 k = u32(kk);
+	u32 j = u32(jj);
+	u32 g = window_group(woff, G, j);
+	u32 k = groups[g].cand_begin + (j - woff[g]);
 	if (status[k] != Status_Performed)
 		return;
 	u32 c = sorted_cand[k];
-	u32 g = cand_group[c];
 	if (k >= groups[g].cut)
 	{
 		u32 i0 = cand_v0[c];
@@ -1616,12 +1656,14 @@ KERNEL k_cut_apply(const u32* __restrict__ sorted_cand, u8* status, const u32* _
 }
 
 // updateQuadrics (simplifier.cpp:1658-1698), one thread per accepted collapse; wedges are merged in ascending vertex order
-KERNEL k_update_quadrics(const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0, const u32* __restrict__ remap, const u32* __restrict__ wedge,
-    const u32* __restrict__ collapse_remap, Quadric* vertex_quadrics, Quadric* attribute_quadrics, QuadricGrad* attribute_gradients, u32 attribute_count, u32 cand_total)
+KERNEL k_update_quadrics(const u32* __restrict__ woff, const GroupState* __restrict__ groups, u32 G, u32 W, const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0,
+    const u32* __restrict__ remap, const u32* __restrict__ wedge, const u32* __restrict__ collapse_remap, Quadric* vertex_quadrics, Quadric* attribute_quadrics, QuadricGrad* attribute_gradients, u32 attribute_count)
 {
-	size_t k = GTID;
-	if (k >= cand_total)
+	size_t jj = GTID;
+	if (jj >= W)
 		return;
+	u32 g = window_group(woff, G, u32(jj));
+	u32 k = groups[g].cand_begin + (u32(jj) - woff[g]);
 	if (status[k] != Status_Performed)
 		return;
 	u32 i0 = cand_v0[sorted_cand[k]];
@@ -2627,6 +2669,8 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		u32 rounds = 0;
 		LAUNCH(k_window_init, G, groups, G);
 		ArenaScope pass_scope(temp);
+		u32* woff = temp.alloc<u32>(size_t(G) + 2); // window offsets of the examined prefixes (see k_window_lengths)
+		u32 W = 0;
 #ifdef CLODB_EMU
 		u32* wave_list[2] = {tri_weight, flip_flag}; // the cut-scan inputs are not live during the rounds: reuse them as work lists
 #else
@@ -2690,12 +2734,15 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 			}
 #endif
 
-			// ---- where would the serial scan have stopped?
-			LAUNCH(k_cut_inputs, cand_total, sort_val, status, cand_v0, cand_group, cand_error, kind, tri_weight, flip_flag, tagged_error, cand_total);
-			exclusive_scan_u32(tri_weight, tri_weight, cand_total, nullptr, temp);
-			exclusive_scan_u32(flip_flag, flip_flag, cand_total, nullptr, temp);
-			exclusive_scan<u64, OpMaxU64>(tagged_error, tagged_error, cand_total, nullptr, temp);
-			LAUNCH(k_cut_find, cand_total, sort_val, status, cand_group, cand_error, groups, tri_weight, flip_flag, tagged_error, cand_total);
+			// ---- where would the serial scan have stopped? (over the examined prefixes only)
+			LAUNCH(k_window_lengths, size_t(G) + 1, groups, G, woff);
+			exclusive_scan_u32(woff, woff, size_t(G) + 1, scalars, temp);
+			W = dev_read(scalars);
+			LAUNCH(k_cut_inputs, W, woff, groups, G, W, sort_val, status, cand_v0, cand_error, kind, tri_weight, flip_flag, tagged_error);
+			exclusive_scan_u32(tri_weight, tri_weight, W, nullptr, temp);
+			exclusive_scan_u32(flip_flag, flip_flag, W, nullptr, temp);
+			exclusive_scan<u64, OpMaxU64>(tagged_error, tagged_error, W, nullptr, temp);
+			LAUNCH(k_cut_find, W, woff, G, W, sort_val, status, cand_error, groups, tri_weight, flip_flag, tagged_error);
 			dev_memset(scalars + 3, 0, sizeof(u32));
 			LAUNCH(k_window_check, G, groups, G, scalars + 3);
 			if (dev_read(scalars + 3) == 0)
@@ -2722,9 +2769,9 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		}
 		dev_memset(group_collapses, 0, size_t(G) * 4);
 		dev_memset(group_error_bits, 0, size_t(G) * 4);
-		LAUNCH(k_cut_apply, cand_total, sort_val, status, cand_v0, cand_group, cand_error, wedge, kind, groups, group_collapses, group_error_bits, collapse_remap, cand_total);
+		LAUNCH(k_cut_apply, W, woff, G, W, sort_val, status, cand_v0, cand_error, wedge, kind, groups, group_collapses, group_error_bits, collapse_remap);
 
-		LAUNCH(k_update_quadrics, cand_total, sort_val, status, cand_v0, remap, wedge, collapse_remap, vertex_quadrics, attribute_quadrics, attribute_gradients, A, cand_total);
+		LAUNCH(k_update_quadrics, W, woff, groups, G, W, sort_val, status, cand_v0, remap, wedge, collapse_remap, vertex_quadrics, attribute_quadrics, attribute_gradients, A);
 		LAUNCH(k_remap_loops, vertex_count, loop, loop_alt, collapse_remap, vertex_count);
 		LAUNCH(k_remap_loops, vertex_count, loopback, loopback_alt, collapse_remap, vertex_count);
 		std::swap(loop, loop_alt);
