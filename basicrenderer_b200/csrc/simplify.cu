@@ -970,6 +970,40 @@ KERNEL k_rank(u32* cand_v0, u32* cand_v1, const u8* __restrict__ cand_bidi, cons
 	sort_val[ci] = u32(ci);
 }
 
+// ---- the examined prefixes as one dense index space ---------------------------------------------------------------------
+// Everything after the wavefront (the cut scans, the roll-back, the quadric updates) only concerns the sorted positions the
+// wavefront has examined: per group the prefix [cand_begin, win_end) of its candidates, typically a third of the list. Those
+// prefixes are laid end to end: window position j of group g <-> sorted position cand_begin[g] + (j - woff[g]). The kernels below
+// run over j in [0, W) and find their group by a binary search over the G + 1 offsets (cache resident).
+KERNEL k_window_lengths(const GroupState* __restrict__ groups, u32 G, u32* lengths)
+{
+	size_t g = GTID;
+	if (g > G)
+		return;
+	u32 len = 0;
+	if (g < G)
+	{
+		const GroupState& gs = groups[g];
+		if (gs.active && gs.cand_count)
+			len = gs.win_end - gs.cand_begin;
+	}
+	lengths[g] = len; // lengths[G] = 0: after the exclusive scan it holds W
+}
+
+DEVFN u32 window_group(const u32* __restrict__ woff, u32 G, u32 j)
+{
+	u32 lo = 0, hi = G;
+	while (hi - lo > 1)
+	{
+		u32 mid = (lo + hi) / 2;
+		if (woff[mid] <= j)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
 // ------------------------------------------------------------------------------------- pass: greedy collapse wavefront
 KERNEL k_collapse_init(u32* collapse_remap, u8* collapse_locked, u32 vertex_count)
 {
@@ -1145,21 +1179,25 @@ DEVFN void wave_publish_entry(const WaveEntry& e, u64* vmin_any, u64* vmin_src, 
 	atomicMin(reinterpret_cast<unsigned long long*>(&vmin_src[e.r0]), value);
 }
 
-// lists the undecided candidates of the current windows as records and publishes them for the first round
-static __global__ void __launch_bounds__(256) k_wave_list(const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_group, const GroupState* __restrict__ groups, const u8* __restrict__ status,
-    const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, WaveArgs a, u32 cand_total)
+// lists the undecided candidates of the current windows as records and publishes them for the first round; one thread per
+// position of the examined prefixes (window index space, see k_window_lengths)
+static __global__ void __launch_bounds__(256) k_wave_list(const u32* __restrict__ woff, u32 G, u32 W, const u32* __restrict__ sorted_cand, const GroupState* __restrict__ groups, const u8* __restrict__ status,
+    const u32* __restrict__ cand_v0, const u32* __restrict__ cand_v1, const u32* __restrict__ remap, WaveArgs a)
 {
-	size_t kk = GTID;
+	size_t jj = GTID;
 	bool take = false;
 	WaveEntry e = {0, 0, 0, 0};
-	if (kk < cand_total && status[kk] == Status_Undecided)
+	if (jj < W)
 	{
-		u32 c = sorted_cand[kk];
-		const GroupState& gs = groups[cand_group[c]];
-		take = u32(kk) >= gs.win_begin && u32(kk) < gs.win_end;
+		const u32 j = u32(jj);
+		const u32 g = window_group(woff, G, j);
+		const GroupState& gs = groups[g];
+		const u32 k = gs.cand_begin + (j - woff[g]);
+		take = k >= gs.win_begin && status[k] == Status_Undecided; // k < win_end by construction
 		if (take)
 		{
-			e.k = u32(kk);
+			u32 c = sorted_cand[k];
+			e.k = k;
 			e.c = c;
 			e.r0 = remap[cand_v0[c]];
 			e.r1 = remap[cand_v1[c]];
@@ -1520,40 +1558,6 @@ KERNEL k_window_check(GroupState* groups, u32 G, u32* any_extend)
 	}
 }
 
-// ---- the examined prefixes as one dense index space ---------------------------------------------------------------------
-// Everything after the wavefront (the cut scans, the roll-back, the quadric updates) only concerns the sorted positions the
-// wavefront has examined: per group the prefix [cand_begin, win_end) of its candidates, typically a third of the list. Those
-// prefixes are laid end to end: window position j of group g <-> sorted position cand_begin[g] + (j - woff[g]). The kernels below
-// run over j in [0, W) and find their group by a binary search over the G + 1 offsets (cache resident).
-KERNEL k_window_lengths(const GroupState* __restrict__ groups, u32 G, u32* lengths)
-{
-	size_t g = GTID;
-	if (g > G)
-		return;
-	u32 len = 0;
-	if (g < G)
-	{
-		const GroupState& gs = groups[g];
-		if (gs.active && gs.cand_count)
-			len = gs.win_end - gs.cand_begin;
-	}
-	lengths[g] = len; // lengths[G] = 0: after the exclusive scan it holds W
-}
-
-DEVFN u32 window_group(const u32* __restrict__ woff, u32 G, u32 j)
-{
-	u32 lo = 0, hi = G;
-	while (hi - lo > 1)
-	{
-		u32 mid = (lo + hi) / 2;
-		if (woff[mid] <= j)
-			lo = mid;
-		else
-			hi = mid;
-	}
-	return lo;
-}
-
 // per window position: triangle weight / flip flag / tagged error for the prefix scans behind the serial early-outs
 KERNEL k_cut_inputs(const u32* __restrict__ woff, const GroupState* __restrict__ groups, u32 G, u32 W, const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0,
     const float* __restrict__ cand_error, const u8* __restrict__ kind, u32* tri_weight, u32* flip_flag, u64* tagged_error)
@@ -1615,57 +1619,102 @@ KERNEL k_cut_find(const u32* __restrict__ woff, u32 G, u32 W, const u32* __restr
 		atomicMin(&gs.cut, k);
 }
 
-// roll back collapses past the cut, count the accepted ones and fold their errors into the group result
+// roll back collapses past the cut; count the accepted ones per group, fold their errors into the group result and list them
+// (accepted[0..*accepted_count), any order: a vertex takes part in at most one performed collapse per pass, so the quadric
+// updates of different accepted collapses touch different vertices). Counters are updated once per (warp, group).
 KERNEL k_cut_apply(const u32* __restrict__ woff, u32 G, u32 W, const u32* __restrict__ sorted_cand, u8* status, const u32* __restrict__ cand_v0, const float* __restrict__ cand_error,
-    const u32* __restrict__ wedge, const u8* __restrict__ kind, GroupState* groups, u32* group_collapses, u32* group_error_bits, u32* collapse_remap)
+    const u32* __restrict__ wedge, const u8* __restrict__ kind, GroupState* groups, u32* group_collapses, u32* group_error_bits, u32* collapse_remap, u32* accepted, u32* accepted_count)
 {
 	size_t jj = GTID;
-	if (jj >= W)
-		return;
-	u32 j = u32(jj);
-	u32 g = window_group(woff, G, j);
-	u32 k = groups[g].cand_begin + (j - woff[g]);
-	if (status[k] != Status_Performed)
-		return;
-	u32 c = sorted_cand[k];
-	if (k >= groups[g].cut)
+	bool accept = false;
+	u32 g = 0, k = 0, error_bits = 0;
+	if (jj < W)
 	{
-		u32 i0 = cand_v0[c];
-		u8 kd = kind[i0];
-		if (kd == Kind_Complex)
+		u32 j = u32(jj);
+		g = window_group(woff, G, j);
+		k = groups[g].cand_begin + (j - woff[g]);
+		if (status[k] == Status_Performed)
 		{
-			u32 v = i0;
-			do
+			u32 c = sorted_cand[k];
+			if (k >= groups[g].cut)
 			{
-				collapse_remap[v] = v;
-				v = wedge[v];
-			} while (v != i0);
+				u32 i0 = cand_v0[c];
+				u8 kd = kind[i0];
+				if (kd == Kind_Complex)
+				{
+					u32 v = i0;
+					do
+					{
+						collapse_remap[v] = v;
+						v = wedge[v];
+					} while (v != i0);
+				}
+				else if (kd == Kind_Seam)
+				{
+					collapse_remap[i0] = i0;
+					collapse_remap[wedge[i0]] = wedge[i0];
+				}
+				else
+					collapse_remap[i0] = i0;
+				status[k] = Status_Locked;
+			}
+			else
+			{
+				accept = true;
+				error_bits = __float_as_uint(cand_error[c]);
+			}
 		}
-		else if (kd == Kind_Seam)
-		{
-			collapse_remap[i0] = i0;
-			collapse_remap[wedge[i0]] = wedge[i0];
-		}
-		else
-			collapse_remap[i0] = i0;
-		status[k] = Status_Locked;
-		return;
 	}
-	atomicAdd(&group_collapses[g], 1u);
-	atomicMax(&group_error_bits[g], __float_as_uint(cand_error[c]));
+#ifdef CLODB_EMU
+	if (accept)
+	{
+		accepted[atomicAdd(accepted_count, 1u)] = k;
+		atomicAdd(&group_collapses[g], 1u);
+		atomicMax(&group_error_bits[g], error_bits);
+	}
+#else
+	const u32 lane = threadIdx.x & 31;
+	unsigned remaining = __ballot_sync(0xffffffffu, accept);
+	if (remaining)
+	{
+		int leader = __ffs(remaining) - 1;
+		u32 off = 0;
+		if (int(lane) == leader)
+			off = atomicAdd(accepted_count, u32(__popc(remaining)));
+		off = __shfl_sync(0xffffffffu, off, leader);
+		if (accept)
+			accepted[off + __popc(remaining & ((1u << lane) - 1))] = k;
+	}
+	while (remaining)
+	{
+		int leader = __ffs(remaining) - 1;
+		u32 g0 = __shfl_sync(0xffffffffu, g, leader);
+		unsigned same = __ballot_sync(0xffffffffu, accept && g == g0);
+		if (accept && g == g0)
+		{
+			u32 mx = __reduce_max_sync(same, error_bits);
+			if (int(lane) == leader)
+			{
+				atomicAdd(&group_collapses[g0], u32(__popc(same)));
+				atomicMax(&group_error_bits[g0], mx);
+			}
+		}
+		remaining &= ~same;
+	}
+#endif
 }
 
 // updateQuadrics (simplifier.cpp:1658-1698), one thread per accepted collapse; wedges are merged in ascending vertex order
-KERNEL k_update_quadrics(const u32* __restrict__ woff, const GroupState* __restrict__ groups, u32 G, u32 W, const u32* __restrict__ sorted_cand, const u8* __restrict__ status, const u32* __restrict__ cand_v0,
+KERNEL k_update_quadrics(const u32* __restrict__ accepted, const u32* __restrict__ accepted_count, const u32* __restrict__ sorted_cand, const u32* __restrict__ cand_v0,
     const u32* __restrict__ remap, const u32* __restrict__ wedge, const u32* __restrict__ collapse_remap, Quadric* vertex_quadrics, Quadric* attribute_quadrics, QuadricGrad* attribute_gradients, u32 attribute_count)
 {
+	// one thread per ACCEPTED collapse (the list k_cut_apply compacted): every thread that survives the bound check has work, so the
+	// chains of dependent scattered loads of many collapses are in flight together. The grid covers the examined prefixes (an
+	// upper bound known on the host); the list length stays on the device.
 	size_t jj = GTID;
-	if (jj >= W)
+	if (jj >= *accepted_count)
 		return;
-	u32 g = window_group(woff, G, u32(jj));
-	u32 k = groups[g].cand_begin + (u32(jj) - woff[g]);
-	if (status[k] != Status_Performed)
-		return;
+	u32 k = accepted[jj];
 	u32 i0 = cand_v0[sorted_cand[k]];
 	u32 r0 = remap[i0];
 	u32 r1 = remap[collapse_remap[r0]];
@@ -2678,6 +2727,10 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 #endif
 		for (;;)
 		{
+			// ---- the examined prefixes of all groups as one dense index space (k_window_lengths)
+			LAUNCH(k_window_lengths, size_t(G) + 1, groups, G, woff);
+			exclusive_scan_u32(woff, woff, size_t(G) + 1, scalars, temp);
+			W = dev_read(scalars);
 			// ---- wavefront over the current windows
 			dev_memset(wave_state, 0, 3 * sizeof(u32));
 #ifdef CLODB_EMU
@@ -2715,8 +2768,8 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 					dev_memset(wa.round_log, 0, 512 * 4);
 				}
 				static const u32 blocks_per_sm_cap = getenv("CLODB200_WAVE_BLOCKS") ? u32(atoi(getenv("CLODB200_WAVE_BLOCKS"))) : 0u;
-				LAUNCH_GRID(k_wave_list, (cand_total + 255) / 256, 256, sort_val, cand_group, groups, status, cand_v0, cand_v1, remap, wa, cand_total);
-				u32 blocks = std::min<u32>(blocks_per_sm_cap ? std::min(wave_max_blocks, blocks_per_sm_cap) : wave_max_blocks, (cand_total + WAVE_THREADS - 1) / WAVE_THREADS);
+				LAUNCH_GRID(k_wave_list, (W + 255) / 256, 256, woff, G, W, sort_val, groups, status, cand_v0, cand_v1, remap, wa);
+				u32 blocks = std::min<u32>(blocks_per_sm_cap ? std::min(wave_max_blocks, blocks_per_sm_cap) : wave_max_blocks, std::max<u32>(1u, (W + WAVE_THREADS - 1) / WAVE_THREADS));
 				LAUNCH_COOP(k_wave_rounds, blocks, WAVE_THREADS, wa);
 				if (g_profile)
 				{
@@ -2735,9 +2788,6 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 #endif
 
 			// ---- where would the serial scan have stopped? (over the examined prefixes only)
-			LAUNCH(k_window_lengths, size_t(G) + 1, groups, G, woff);
-			exclusive_scan_u32(woff, woff, size_t(G) + 1, scalars, temp);
-			W = dev_read(scalars);
 			LAUNCH(k_cut_inputs, W, woff, groups, G, W, sort_val, status, cand_v0, cand_error, kind, tri_weight, flip_flag, tagged_error);
 			exclusive_scan_u32(tri_weight, tri_weight, W, nullptr, temp);
 			exclusive_scan_u32(flip_flag, flip_flag, W, nullptr, temp);
@@ -2769,9 +2819,11 @@ SimplifyOutput simplify_groups(const u32* gtri, const u32* group_tri_offset_host
 		}
 		dev_memset(group_collapses, 0, size_t(G) * 4);
 		dev_memset(group_error_bits, 0, size_t(G) * 4);
-		LAUNCH(k_cut_apply, W, woff, G, W, sort_val, status, cand_v0, cand_error, wedge, kind, groups, group_collapses, group_error_bits, collapse_remap);
+		u32* accepted = flip_flag; // the cut scans are done with it
+		dev_memset(scalars + 4, 0, sizeof(u32));
+		LAUNCH(k_cut_apply, (size_t(W) + 31) / 32 * 32, woff, G, W, sort_val, status, cand_v0, cand_error, wedge, kind, groups, group_collapses, group_error_bits, collapse_remap, accepted, scalars + 4);
 
-		LAUNCH(k_update_quadrics, W, woff, groups, G, W, sort_val, status, cand_v0, remap, wedge, collapse_remap, vertex_quadrics, attribute_quadrics, attribute_gradients, A);
+		LAUNCH(k_update_quadrics, W, accepted, scalars + 4, sort_val, cand_v0, remap, wedge, collapse_remap, vertex_quadrics, attribute_quadrics, attribute_gradients, A);
 		LAUNCH(k_remap_loops, vertex_count, loop, loop_alt, collapse_remap, vertex_count);
 		LAUNCH(k_remap_loops, vertex_count, loopback, loopback_alt, collapse_remap, vertex_count);
 		std::swap(loop, loop_alt);
