@@ -525,17 +525,26 @@ __global__ void k_rs_hist(const K* __restrict__ keys, u32* __restrict__ counts, 
 	counts[size_t(threadIdx.x) * nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
+// Scatter pass. Ranks come from warp match_any (in-order rank among the warp's items with the same digit) and running bases
+// across the warps of the CTA, as before; what changed is where the keys go first: into shared memory at their position in the
+// tile's digit-sorted order, and from there to global memory with consecutive threads writing consecutive addresses of a
+// (digit, tile) run. The direct version issued one 4-byte store per key to 32 different sectors per warp instruction and ran at a
+// fifth of the bandwidth its DRAM traffic needed (ncu: L2 transaction bound, not DRAM bound).
 template <typename K>
-__global__ void k_rs_scatter(const K* __restrict__ keys, K* __restrict__ keys_out, const u32* __restrict__ vals, u32* __restrict__ vals_out, const u32* __restrict__ offsets, size_t n, int shift, u32 nblocks)
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__ keys, K* __restrict__ keys_out, const u32* __restrict__ vals, u32* __restrict__ vals_out, const u32* __restrict__ offsets, size_t n, int shift, u32 nblocks)
 {
 	__shared__ u32 hist[RS_WARPS][256];
+	__shared__ K s_keys[RS_TILE];
+	__shared__ u32 s_vals[RS_TILE];
+	__shared__ u32 s_goff[256];  // global position of the run of digit d minus its first position in the tile order
+	__shared__ u32 s_warp_total[RS_WARPS];
 	for (int w = 0; w < RS_WARPS; ++w)
 		hist[w][threadIdx.x] = 0;
 	__syncthreads();
 
-	size_t tile = size_t(blockIdx.x) * RS_TILE;
-	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	u32 lt_mask = (1u << lane) - 1;
+	const size_t tile = size_t(blockIdx.x) * RS_TILE;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 lt_mask = (1u << lane) - 1;
 
 	K key[RS_ITEMS];
 	u32 rank[RS_ITEMS];
@@ -564,16 +573,35 @@ __global__ void k_rs_scatter(const K* __restrict__ keys, K* __restrict__ keys_ou
 	}
 	__syncthreads();
 
-	// thread d: running base for digit d across the warps of this CTA (global offset of (digit, tile) first)
+	// thread d: the digit's count in the tile, running bases across the warps, and (block-wide exclusive scan over the digits) the
+	// first position of the digit in the tile's sorted order
 	{
-		u32 d = threadIdx.x;
-		u32 run = offsets[size_t(d) * nblocks + blockIdx.x];
+		const u32 d = threadIdx.x;
+		u32 total = 0;
 		for (int w = 0; w < RS_WARPS; ++w)
 		{
 			u32 c = hist[w][d];
-			hist[w][d] = run;
-			run += c;
+			hist[w][d] = total;
+			total += c;
 		}
+		u32 inc = total;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o)
+				inc += t;
+		}
+		if (lane == 31)
+			s_warp_total[warp] = inc;
+		__syncthreads();
+		u32 before = 0;
+		for (int w = 0; w < warp; ++w)
+			before += s_warp_total[w];
+		const u32 first = before + inc - total; // exclusive prefix over the digits
+		s_goff[d] = offsets[size_t(d) * nblocks + blockIdx.x] - first;
+		for (int w = 0; w < RS_WARPS; ++w)
+			hist[w][d] += first;
 	}
 	__syncthreads();
 
@@ -584,10 +612,26 @@ __global__ void k_rs_scatter(const K* __restrict__ keys, K* __restrict__ keys_ou
 		if (i < n)
 		{
 			u32 digit = u32(key[r] >> shift) & 255u;
-			size_t dst = size_t(hist[warp][digit]) + rank[r];
-			keys_out[dst] = key[r];
+			u32 pos = hist[warp][digit] + rank[r];
+			s_keys[pos] = key[r];
 			if (vals)
-				vals_out[dst] = vals[i];
+				s_vals[pos] = vals[i];
+		}
+	}
+	__syncthreads();
+
+	const u32 count = n - tile < size_t(RS_TILE) ? u32(n - tile) : u32(RS_TILE);
+#pragma unroll
+	for (int q = 0; q < RS_ITEMS; ++q)
+	{
+		u32 pos = u32(q) * RS_THREADS + threadIdx.x;
+		if (pos < count)
+		{
+			K k = s_keys[pos];
+			u32 dst = s_goff[u32(k >> shift) & 255u] + pos;
+			keys_out[dst] = k;
+			if (vals)
+				vals_out[dst] = s_vals[pos];
 		}
 	}
 }

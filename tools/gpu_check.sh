@@ -3,7 +3,7 @@
 # Everything lands in gpurun_out/<tag>_*.
 tag=${1:-check}; shift
 mkdir -p gpurun_out
-python -m pytest tests/test_scale_parity.py tests/test_stages.py tests/test_dag.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${tag}_tests.txt
+python -m pytest tests/test_prims.py tests/test_scale_parity.py tests/test_stages.py tests/test_dag.py tests/test_artifacts.py tests/test_mikk.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${tag}_tests.txt
 cat gpurun_out/${tag}_tests.txt
 CLODB200_BENCH_WORKLOAD=C2 CLODB200_PROFILE_OUT=gpurun_out/${tag}_c2_kernels.csv python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_c2_bench.json 2> gpurun_out/${tag}_c2_bench.err
 python - <<PY
