@@ -15,6 +15,7 @@
 #include "artifacts.h"
 
 #include <chrono>
+#include <memory>
 
 #include <algorithm>
 #include <cfloat>
@@ -1085,6 +1086,13 @@ struct ArtifactSink : DagSink
 	{
 		const u32 level = u32(level_tri.size() - 1);
 		const size_t base_group = groups.size(), base_meshlet = meshlets.size();
+		if (base_meshlet == 0)
+		{
+			// the DAG halves per level: all levels together hold about twice the clusters of the first. Growing the vectors level by
+			// level would copy tens of MB at every reallocation.
+			meshlets.reserve(size_t(b.cluster_count) * 2 + size_t(b.cluster_count) / 4 + 1024);
+			groups.reserve(size_t(b.group_count) * 2 + size_t(b.group_count) / 2 + 64);
+		}
 		groups.resize(base_group + b.group_count);
 		meshlets.resize(base_meshlet + b.cluster_count);
 		host_parallel_for(b.group_count, 16, [&](size_t g_begin, size_t g_end, size_t) {
@@ -1535,8 +1543,11 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	ArenaScope scope(temp);
 
 	// jobs in group-bucket order; placement fields are filled after the packing below
-	std::vector<MeshletJob> jobs(M);
-	std::vector<u32> group_of(M);
+	// not value-initialised: every element is written (memset included) by the parallel fill below
+	std::unique_ptr<MeshletJob[]> jobs_storage(new MeshletJob[M]);
+	MeshletJob* const jobs = jobs_storage.get();
+	std::unique_ptr<u32[]> group_of_storage(new u32[M]);
+	u32* const group_of = group_of_storage.get();
 	size_t vertex_refs = 0, triangle_total = 0;
 	host_parallel_for(G, 64, [&](size_t g_begin, size_t g_end, size_t) {
 		for (u32 g = u32(g_begin); g < u32(g_end); ++g)
@@ -1591,7 +1602,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	lap("bucket order + jobs (host)");
 	// ---- device pre-pass: distinct vertices per group, UV ranges per meshlet
 	MeshletJob* d_jobs = temp.alloc<MeshletJob>(M);
-	dev_h2d(d_jobs, jobs.data(), size_t(M) * sizeof(MeshletJob));
+	dev_h2d(d_jobs, jobs, size_t(M) * sizeof(MeshletJob));
 	u64 table_size = 1;
 	while (table_size < u64(vertex_refs) * 2 + 16)
 		table_size <<= 1;
@@ -1918,7 +1929,7 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 	PageRecord* d_pages = temp.alloc<PageRecord>(page_count);
 	UvJob* d_uv_jobs = temp.alloc<UvJob>(size_t(M) * std::max(U, 1u));
 	dev_memset(d_out, 0, total_bytes);
-	dev_h2d(d_jobs, jobs.data(), size_t(M) * sizeof(MeshletJob));
+	dev_h2d(d_jobs, jobs, size_t(M) * sizeof(MeshletJob));
 	dev_h2d(d_pages, pages.data(), size_t(page_count) * sizeof(PageRecord));
 	if (U)
 		dev_h2d(d_uv_jobs, uv_jobs.data(), uv_jobs.size() * sizeof(UvJob));
