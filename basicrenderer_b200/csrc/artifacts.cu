@@ -1544,8 +1544,11 @@ void build_artifacts(const DeviceGeometry& geo, const BuilderSettings& settings,
 
 	// jobs in group-bucket order; placement fields are filled after the packing below
 	// not value-initialised: every element is written (memset included) by the parallel fill below
-	std::unique_ptr<MeshletJob[]> jobs_storage(new MeshletJob[M]);
-	MeshletJob* const jobs = jobs_storage.get();
+	// ... and in the workspace's pinned staging buffer (idle once the DAG is built: the level downloads have been consumed), because
+	// the array is uploaded twice (128 MB on C3)
+	dev_d2h_async_wait();
+	ws.stage.reserve(size_t(M) * sizeof(MeshletJob) + 256);
+	MeshletJob* const jobs = reinterpret_cast<MeshletJob*>(ws.stage.base);
 	std::unique_ptr<u32[]> group_of_storage(new u32[M]);
 	u32* const group_of = group_of_storage.get();
 	size_t vertex_refs = 0, triangle_total = 0;

@@ -1080,12 +1080,17 @@ static __global__ void __launch_bounds__(PT_THREADS) k_partition_chained(Partiti
 }
 #endif
 
-KERNEL k_split_flags(const u32* __restrict__ node_split, u32* flags, u32 n_nodes)
+// children numbering input; also tells (any_large) whether some child will still be above the meshlet size, i.e. whether the next
+// tree level needs the SAH sweeps: known as soon as the splits are, so it travels to the host with the split count in one read
+KERNEL k_split_flags(const u32* __restrict__ node_split, const u32* __restrict__ node_count, u32* flags, u32 n_nodes, u32 max_triangles, u32* any_large)
 {
 	size_t n = GTID;
 	if (n >= n_nodes)
 		return;
-	flags[n] = node_split[n] ? 1u : 0u;
+	u32 split = node_split[n];
+	flags[n] = split ? 1u : 0u;
+	if (split && (split > max_triangles || node_count[n] - split > max_triangles))
+		atomicOr(any_large, 1u);
 }
 
 KERNEL k_make_children(const u32* __restrict__ node_begin, const u32* __restrict__ node_count, const u32* __restrict__ node_split, const u32* __restrict__ child_rank,
@@ -1615,9 +1620,12 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 #endif
 
 		// children numbering
-		LAUNCH(k_split_flags, n_nodes, node_split, node_flags, n_nodes);
+		dev_memset(node_total_dev + 1, 0, sizeof(u32));
+		LAUNCH(k_split_flags, n_nodes, node_split, node_count, node_flags, n_nodes, sp.max_triangles, node_total_dev + 1);
 		exclusive_scan_u32(node_flags, node_flags, n_nodes, node_total_dev, temp);
-		u32 n_split = dev_read(node_total_dev);
+		// one read-back per tree level: {number of nodes that split, any child still above the meshlet size}
+		std::vector<u32> level_words = dev_download(node_total_dev, 2);
+		u32 n_split = level_words[0];
 		if (n_split == 0)
 			break;
 
@@ -1637,8 +1645,7 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 			LAUNCH_GRID(k_partition_chained, size_t(tiles) * 3, PT_THREADS, pa, node_of_pos, node_begin, node_split, side, T, tiles, g_scan_chain.desc, epoch);
 		}
 #endif
-		dev_memset(node_total_dev + 1, 0, sizeof(u32));
-		LAUNCH(k_make_children, n_nodes, node_begin, node_count, node_split, node_flags, node_begin_alt, node_count_alt, n_nodes, sp.max_triangles, node_total_dev + 1);
+		LAUNCH(k_make_children, n_nodes, node_begin, node_count, node_split, node_flags, node_begin_alt, node_count_alt, n_nodes, sp.max_triangles, node_total_dev + 2);
 		LAUNCH(k_update_node_of_pos, T, node_of_pos, node_begin, node_split, node_flags, node_of_pos_alt, T);
 
 		for (int k = 0; k < 3; ++k)
@@ -1647,7 +1654,7 @@ ClusterSet clusterize(const u32* tri, u32 T, const u32* seg_offsets_host, u32 S,
 		std::swap(node_count, node_count_alt);
 		std::swap(node_of_pos, node_of_pos_alt);
 		n_nodes = n_split * 2;
-		any_large = dev_read(node_total_dev + 1) != 0;
+		any_large = level_words[1] != 0;
 		if (depth > kMeshletMaxTreeDepth + 2)
 			throw Error("clodb200: clusterize exceeded the tree depth limit");
 	}
