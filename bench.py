@@ -73,8 +73,9 @@ KERNEL_BYTES_PER_THREAD = {
     "k_cut_find": 29,
     "k_cut_inputs": 4 + 1 + 4 + 4 + 4 + 1 + 4 + 4 + 8,
     "k_cut_apply": 4 + 1 + 4 + 4,
-    # listing pass: status 1 + sorted id 4 + group 4 per candidate (the gathers and the record only for listed candidates)
-    "k_wave_list": 9,
+    # listing pass, one thread per examined position: status 1 + window offsets (cached) + for listed candidates sorted id 4, endpoints 8,
+    # position classes 8, record 16, three publishes 24 (about 40 % of the positions are listed)
+    "k_wave_list": 1 + 24,
     "k_pick_flags": 4 + 4 + 4 + 4 + 2 + 4,
     "k_pick_emit": 4 + 4 + 4,
     "k_adj_count": 4 + 4,
@@ -83,7 +84,8 @@ KERNEL_BYTES_PER_THREAD = {
 
 # Kernels without a byte model are not bandwidth kernels; what bounds them, from the ncu captures in profiles/r02_ncu_kernels.md
 KERNEL_LIMITER = {
-    "k_update_quadrics": "latency: one thread per candidate, the ~8 % that were performed run a chain of dependent scattered read-modify-writes of 44..156-byte quadrics (long_scoreboard 520 warps per issue)",
+    "k_update_quadrics": "latency: one thread per accepted collapse (compacted list), each a chain of dependent scattered read-modify-writes of 44..156-byte quadrics",
+    "k_fill_attribute_quadrics": "gather + compute: per vertex, the attribute quadrics and gradients of its adjacent triangles in corner order (the reference's summation order)",
     "k_merge_rounds": "latency + grid barriers: persistent cooperative kernel, 6 barriers per merge round over a shrinking edge list (barrier 55 warps per issue)",
     "k_build_clusters_warp": "compute: meshlet assembly + optimizeMeshlet per warp, SM throughput 88 %",
     "k_cluster_bounds_warp": "compute: 7-axis extremal search + sequential sphere growth per cluster",
