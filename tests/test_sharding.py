@@ -127,3 +127,66 @@ def test_scene_batch_world_size_2_gloo_real_builds(tmp_path):
         a = lib.build_artifacts(art.interleave(m.positions, m.normals), m.indices, art.VERTEX_NORMALS, keep_handle=True)
         assert lib.serialize_metadata(a, f"clod_mesh{i}.clodbin", "scene", f"/mesh{i}") == blob
         lib.free_artifacts(a)
+
+
+def test_library_gather_loopback_and_errors(lib):
+    """csrc/comm.cu with world size 1 (no NCCL involved): the gather returns this rank's payload; a second init is refused; the
+    emulation refuses world sizes above 1 (it has no NCCL), the CUDA library needs a 128-byte id for them."""
+    from basicrenderer_b200 import ClodbError
+
+    lib.comm_init(None, 1, 0)
+    try:
+        h = sharding.gather_metadata_begin(lib, [3, 5], [b"abc", b"defgh"])
+        assert sharding.gather_metadata_end(lib, h) == {3: b"abc", 5: b"defgh"}
+        assert lib.gather_end(lib.gather_begin(b"")) == [b""]
+    finally:
+        lib.comm_destroy()
+    import pytest
+
+    with pytest.raises(ClodbError):
+        lib.comm_init(None, 2, 0)  # more than one rank needs the unique id
+    with pytest.raises(ClodbError):
+        lib.comm_init(b"\0" * 128, 2, 5)  # rank out of range
+    lib.comm_destroy()
+
+
+@__import__("pytest").mark.gpu
+def test_library_gather_two_ranks_nccl(tmp_path):
+    """Two processes on one or two GPUs exchange payloads of different sizes through clodb200_comm* (NCCL all-gather over the
+    library's own communicator); skipped when fewer than two GPUs are visible."""
+    import pytest
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys, pickle, time
+        sys.path.insert(0, "@ROOT@")
+        from basicrenderer_b200 import load, sharding
+        rank = int(sys.argv[1])
+        lib = load(rank)
+        idf = os.path.join("@OUT@", "id.bin")
+        if rank == 0:
+            open(idf + ".tmp", "wb").write(lib.comm_unique_id()); os.replace(idf + ".tmp", idf)
+        while not os.path.exists(idf):
+            time.sleep(0.05)
+        lib.comm_init(open(idf, "rb").read(), 2, rank)
+        out = []
+        for rnd in range(3):
+            ids = [10 * rank + i for i in range(2 + rank)]
+            blobs = [bytes([rank + 1]) * (1000 * (i + 1) + 7 * rnd + rank) for i in range(2 + rank)]
+            out.append(sharding.gather_metadata_end(lib, sharding.gather_metadata_begin(lib, ids, blobs)))
+        lib.comm_destroy()
+        pickle.dump(out, open(os.path.join("@OUT@", f"out{rank}.pkl"), "wb"))
+    """).replace("@ROOT@", ROOT).replace("@OUT@", str(tmp_path)))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    import pickle
+
+    a, b = (pickle.load(open(tmp_path / f"out{r}.pkl", "rb")) for r in range(2))
+    assert a == b and len(a) == 3
+    for rnd, merged in enumerate(a):
+        assert sorted(merged) == [0, 1, 10, 11, 12]
+        assert merged[11] == bytes([2]) * (2000 + 7 * rnd + 1)
