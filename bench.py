@@ -236,9 +236,10 @@ def _comm_setup(lib, rank, world):
     box = [lib.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     lib.comm_init(box[0], world, rank)
-    # warm-up exchange: NCCL sets its channels up lazily inside the first collective of a communicator (hundreds of ms)
-    for _ in range(2):
-        lib.gather_end(lib.gather_begin(b"warm-up %d" % rank))
+    # warm-up exchanges: NCCL sets its channels up lazily inside the first collective of a communicator (hundreds of ms), and again
+    # when a message is large enough to change protocol; the batch gather carries a few MB per rank
+    for size in (16, 1 << 20, 24 << 20):
+        lib.gather_end(lib.gather_begin(bytes(size)))
 
 
 def _timed_builds(lib, steps, build_once, rank, world):
