@@ -1,7 +1,8 @@
 """Scene batches across GPUs: meshes are independent units (reference: one task per primitive,
 BasicRenderer/src/Import/GlTFGeometryExtractor.cpp:1349), so a batch is sharded by mesh with no data-path collective.
-The only exchange is the gather of the per-mesh metadata blobs to rank 0; page/cluster payloads stay on
-the rank that built them. torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests)."""
+The only exchange is the gather of the per-mesh metadata blobs; page/cluster payloads stay on the rank that built
+them. On GPUs the gather is the library's own NCCL all-gather (csrc/comm.cu: gather_metadata_begin / gather_metadata_end below);
+gather_metadata is the torch.distributed version kept for the world-size-2 gloo tests on CPU."""
 from __future__ import annotations
 
 import math
