@@ -353,7 +353,8 @@ struct MergeArgs
 	u32* table_w;
 	u64 *best_key, *claim;
 	u32 *best_w, *parent;
-	u32* state; // [0] edges in list 0 on entry, [1] edge counter of the next list, [2] smallest open size, [3] merges of the round, [4] rounds run
+	u32* state; // [0] edges in list 0 on entry, [1] edge counter of the next list, [2] smallest open size, [3] merges of the round, [4] rounds run,
+	            // [5] which list holds the final contracted graph, [6] its edge count
 	u32 K, target, max_size, max_rounds;
 	int use_bounds;
 };
@@ -377,7 +378,9 @@ DEVFN bool pick_key_of_edge(const MergeArgs& a, int cur, u32 e, u32* g_out, u64*
 	if (me.size == 0 || me.size >= a.target)
 		return false;
 	const GroupInfo other = a.info[h];
-	if (other.size == 0 || other.size >= a.target)
+	// a neighbour that has reached the target size still absorbs small groups while the sum fits the maximum: the reference only
+	// finalises a group when it is popped off the heap, and large groups are popped last (partition.cpp:556-566)
+	if (other.size == 0)
 		return false;
 	if (me.size + other.size > a.max_size)
 		return false;
@@ -573,6 +576,8 @@ static void merge_rounds(MergeArgs a, u32 E)
 		cur ^= 1;
 	}
 	a.state[4] = rounds;
+	a.state[5] = u32(cur);
+	a.state[6] = E;
 }
 #else
 static const int MERGE_THREADS = 512;
@@ -672,7 +677,11 @@ static __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_rounds(MergeA
 		cur = nxt;
 	}
 	if (gtid == 0)
+	{
 		a.state[4] = rounds;
+		a.state[5] = u32(cur);
+		a.state[6] = E;
+	}
 }
 
 static void merge_rounds(MergeArgs a, u32 E)
@@ -694,7 +703,15 @@ static void merge_rounds(MergeArgs a, u32 E)
 
 // spatial merge of the leftover small groups along the Morton order of their centres (replaces mergeSpatial's kd-tree
 // leaves, partition.cpp:368-480): each still-open group looks at its nearest open neighbours in that order
-KERNEL k_leftover_pick(const GroupInfo* __restrict__ info, const u32* __restrict__ order, u32 n, u32 target, u32 max_size, u32* best)
+// groups that still have a neighbour in the contracted graph
+KERNEL k_mark_connected(const u32* __restrict__ edge_src, u32 E, u32* isolated)
+{
+	size_t e = GTID;
+	if (e < E)
+		isolated[edge_src[e]] = 0;
+}
+
+KERNEL k_leftover_pick(const GroupInfo* __restrict__ info, const u32* __restrict__ order, const u32* __restrict__ isolated, u32 n, u32 target, u32 max_size, u32* best)
 {
 	size_t p = GTID;
 	if (p >= n)
@@ -702,7 +719,7 @@ KERNEL k_leftover_pick(const GroupInfo* __restrict__ info, const u32* __restrict
 	u32 g = order[p];
 	best[g] = NONE;
 	const GroupInfo& me = info[g];
-	if (me.size == 0 || me.size >= target)
+	if (me.size == 0 || me.size >= target || !isolated[g])
 		return;
 	float best_score = -1.f;
 	u32 best_h = NONE;
@@ -715,7 +732,7 @@ KERNEL k_leftover_pick(const GroupInfo* __restrict__ info, const u32* __restrict
 			continue;
 		u32 h = order[q];
 		const GroupInfo& other = info[h];
-		if (other.size == 0 || me.size + other.size > max_size)
+		if (other.size == 0 || me.size + other.size > max_size || !isolated[h])
 			continue;
 		float score = g < h ? merge_score(me, other, 1, true) : merge_score(other, me, 1, true);
 		if (score > best_score || (score == best_score && h < best_h))
@@ -1216,6 +1233,8 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 		LAUNCH(k_edge_combine, E0, e_key, nullptr, e_flag, E, E0, u64(K), e_src, e_dst, e_w);
 	}
 	// ---- merge rounds: one persistent kernel, no host round trip (state: see MergeArgs)
+	u32* final_src[2] = {nullptr, nullptr};
+	bool have_graph = false;
 	if (E > 0)
 	{
 		size_t table_cap = 2;
@@ -1239,14 +1258,28 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 		dev_memset(ma.best_key, 0, size_t(K) * sizeof(u64));
 		dev_memset(claim, 0, size_t(K) * sizeof(u64));
 		iota(parent, K);
-		u32 st[5] = {E, 0, 0xffffffffu, 0, 0};
+		u32 st[7] = {E, 0, 0xffffffffu, 0, 0, 0, E};
 		dev_h2d(ma.state, st, sizeof(st));
 		merge_rounds(ma, E);
+		final_src[0] = ma.src[0], final_src[1] = ma.src[1];
+		have_graph = true;
 	}
 
-	// ---- leftovers: spatially merge open groups (only when positions are used, partition.cpp:599-611)
+	// ---- leftovers: spatially merge open groups (only when positions are used, partition.cpp:599-611) - but only groups that have
+	// no neighbour left in the contracted graph (separate components: islands, soups). An open group that is still surrounded by
+	// neighbours which cannot take it stays a smaller group: pairing it with a non-adjacent group nearby gives a group of two
+	// separate patches, each with its own locked border, and those were the groups with the largest simplification errors
+	// (3 of 70 on a 3.4 M-triangle heightfield, all three at the top of the error ranking; the reference's kd-tree leaves produce 1).
 	if (config.partition_spatial)
 	{
+		u32* isolated = temp.alloc<u32>(K);
+		fill(isolated, 1u, K);
+		if (have_graph)
+		{
+			std::vector<u32> final_state = dev_download(scalars + 8, 7);
+			if (final_state[6])
+				LAUNCH(k_mark_connected, final_state[6], final_src[final_state[5] & 1], final_state[6], isolated);
+		}
 		u32* flags = temp.alloc<u32>(size_t(K) + 1);
 		u64* mkeys = temp.alloc<u64>(K);
 		u64* mkeys_tmp = temp.alloc<u64>(K);
@@ -1274,7 +1307,7 @@ GroupSet partition_clusters(const u32* tri, const u32* cluster_tri_offset, u32 K
 			radix_sort_pairs<u64>(mkeys, mkeys_tmp, mvals, mvals_tmp, live, 0, 50, temp);
 			LAUNCH(k_gather_ids, live, root_ids, mvals, order, live);
 			fill(best, NONE, K);
-			LAUNCH(k_leftover_pick, live, info, order, live, target, max_size, best);
+			LAUNCH(k_leftover_pick, live, info, order, isolated, live, target, max_size, best);
 			iota(parent, K);
 			dev_memset(scalars + 1, 0, sizeof(u32));
 			u32* lclaim = temp.alloc<u32>(K);
