@@ -34,7 +34,15 @@ extern "C"
 #define CLODB200_ERR_INVALID (-2)
 #define CLODB200_ERR_RUNTIME (-3)
 
-/* Same layout as struct clodConfig, clusterlod.h:15-71. */
+/* Same layout as struct clodConfig, clusterlod.h:15-71 (a memcpy of the reference's struct is valid).
+ * Supported subset: every field the reference's builder sets (ClusterLODUtilities.cpp:5426-5460) - max_vertices / max_triangles /
+ * min_triangles (1..256), partition_spatial, partition_sort, partition_size, partition_max_refined_groups,
+ * partition_refined_split_count (incremented once per split partition), cluster_spatial = true, cluster_fill_weight, simplify_ratio,
+ * simplify_threshold, simplify_error_merge_previous / _additive, simplify_error_factor_sloppy, simplify_permissive,
+ * simplify_fallback_sloppy, optimize_bounds, optimize_clusters. Values whose reference behaviour is not built make the build fail with
+ * an error instead of being ignored: cluster_spatial = false (meshopt_buildMeshletsFlex; note that clodDefaultConfig() leaves it
+ * false, clusterlod.h:762), simplify_regularize, simplify_fallback_permissive without simplify_permissive,
+ * simplify_error_edge_limit > 0. cluster_split_factor only matters for the flex clusterizer and is ignored. */
 typedef struct clodb200_config
 {
 	size_t max_vertices;
